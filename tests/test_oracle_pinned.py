@@ -1,0 +1,123 @@
+"""Pins oracle/cmunet_oracle.py (plain-torch restatement) against golden vectors minted by executing the
+unmodified reference (oracle/make_goldens.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cmunet_oracle as O
+
+G = os.path.join(os.path.dirname(__file__), 'golden')
+PRE = json.load(open(os.path.join(G, 'pretrain.json')))['cases']
+FT = json.load(open(os.path.join(G, 'finetune.json')))['case']
+MOD = json.load(open(os.path.join(G, 'modules.json')))['cases']
+
+
+def check_fp(t, fp, rtol=2e-4, atol=1e-6):
+    t = t.detach().double().flatten().cpu()
+    scale = max(fp['norm'], 1e-30)
+    assert abs(float(t.norm()) - fp['norm']) <= rtol * scale + atol, (float(t.norm()), fp['norm'])
+    vals = t[torch.tensor(fp['idx'])].numpy()
+    np.testing.assert_allclose(vals, np.array(fp['val']), rtol=rtol * 50, atol=atol + 2e-4 * scale / max(1.0, t.numel() ** 0.5))
+
+
+def run_pretrain_case(c):
+    torch.manual_seed(c['seed'])
+    m = O.OracleCMUNet(img_size=c['S'], np_seed=c['seed'])
+    m.init_weights()
+    m.train()
+    assert [k for k, _ in m.named_parameters()] == c['param_keys']
+    assert sum(p.numel() for p in m.parameters()) == c['n_params']
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == c['n_trainable']
+    for k, p in m.named_parameters():
+        check_fp(p, c['init'][k], rtol=1e-6)
+    img, img_t = O.synthetic_batch(c['B'], c['S'], c['data_seed'])
+    torch.manual_seed(c['seed'] + 1000)
+    out = m(img, mode='loss', img_t=img_t)
+    assert float(out['loss_ct']) == pytest.approx(c['loss_ct'], rel=1e-4)
+    assert float(out['loss_rc']) == pytest.approx(c['loss_rc'], rel=1e-4)
+    (out['loss_ct'] + out['loss_rc']).backward()
+    assert sorted(k for k, p in m.named_parameters() if p.grad is None) == sorted(c['no_grad_keys'])
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            check_fp(p.grad, c['grad'][k], rtol=2e-3)
+    for k, b in m.named_buffers():
+        check_fp(b.float(), c['buffers_after'][k], rtol=1e-4)
+    m.momentum_update()
+    for k, p in m.named_parameters():
+        if k.startswith('target_'):
+            check_fp(p, c['target_after_ema'][k], rtol=1e-6)
+
+
+def test_pretrain_S64():
+    run_pretrain_case(PRE[0])
+
+
+def test_pretrain_S224_reference_native():
+    run_pretrain_case(PRE[1])
+
+
+@pytest.mark.slow
+def test_pretrain_S512():
+    run_pretrain_case(PRE[2])
+
+
+def test_finetune_config1():
+    c = FT
+    torch.manual_seed(c['seed'])
+    net = O.OracleUNet().train()
+    for k, p in net.named_parameters():
+        check_fp(p, c['init'][k], rtol=1e-6)
+    x = torch.rand(4, 256, 256)
+    y1 = (torch.rand(4, 1, 256, 256) > 0.9)
+    y = torch.cat([~y1, y1], 1).double()
+    pred = net(x)
+    check_fp(pred, c['pred'], rtol=1e-4)
+    dice, ce, iou = O.dice_loss(pred, y), O.ce_prob_loss(pred, y), O.iou_loss(pred, y)
+    assert float(dice) == pytest.approx(c['dice_loss'], rel=1e-6)
+    assert float(ce) == pytest.approx(c['ce_loss'], rel=1e-5)
+    assert float(iou) == pytest.approx(c['iou_loss'], rel=1e-6)
+    total = dice + ce
+    assert str(total.dtype) == c['total_dtype'] == 'torch.float64'
+    assert not dice.requires_grad and c['dice_requires_grad'] is False      # Q7
+    total.backward()
+    for k, p in net.named_parameters():
+        check_fp(p.grad, c['grad'][k], rtol=2e-3)
+    net.eval()
+    with torch.no_grad():
+        check_fp(net(x), c['pred_eval'], rtol=1e-4)
+
+
+def test_module_double_conv():
+    c = MOD['double_conv']
+    torch.manual_seed(c['seed'])
+    dc = O._DC(8, 16).train()
+    x = torch.randn(2, 8, 12, 20, requires_grad=True)
+    y = O.double_conv_fwd(dc, x)
+    (y * torch.linspace(0, 1, y.numel()).view_as(y)).sum().backward()
+    check_fp(y, c['out'])
+    check_fp(x.grad, c['dx'], rtol=1e-3)
+    for k, p in dc.named_parameters():
+        check_fp(p.grad, c['grads'][k], rtol=1e-3, atol=1e-4)
+    for k, b in dc.named_buffers():
+        check_fp(b.float(), c['buffers'][k])
+
+
+def test_module_head():
+    c = MOD['head']
+    torch.manual_seed(c['seed'])
+    head = O.OracleHead().train()
+    B, S = c['B'], c['S']
+    img = torch.randn(B, S, S)
+    pred = torch.randn(B, 2, S, S, requires_grad=True)
+    mask = (torch.rand(B, S, S) > 0.4).to(torch.uint8)
+    ps = torch.randn(B, 1, 256, requires_grad=True)
+    pt = torch.randn(B, 1, 256)
+    out = head(img, pred[:, 1], mask, ps, pt)
+    assert float(out['loss_ct']) == pytest.approx(c['loss_ct'], rel=1e-5)
+    assert float(out['loss_rc']) == pytest.approx(c['loss_rc'], rel=1e-5)
+    (out['loss_ct'] + out['loss_rc']).backward()
+    check_fp(pred.grad, c['d_pred'])
+    check_fp(ps.grad, c['d_proj_s'], rtol=1e-3)
