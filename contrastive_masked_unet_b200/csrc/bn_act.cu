@@ -1,0 +1,588 @@
+// HBM-bound kernels around the tensor-core convolutions: weight packing, the Cin=1 first convolution (fused with
+// the patch-mask multiply), BatchNorm statistics finalisation, BN-apply + ReLU (+ 2x2 max-pool), and the
+// BatchNorm/ReLU/max-pool backward passes.  All activations are NHWC bf16; every thread moves 16-byte vectors
+// (8 channels) so that warps read/write whole 128-byte lines.
+#include "common.cuh"
+#include "../../include/cmu_b200.h"
+
+namespace cmu {
+
+struct bf16x8 {
+  uint4 u;
+};
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+// ---------------------------------------------------------------------------------- weight packing
+// torch Conv2d weight (Cout, Cin, 3, 3) fp32 ->
+//   wf[t = s*3 + r][co][ci]   (fprop B operand, K-major)         t indexes kernel column s first (see tc_conv.cu)
+//   wd[t' = s'*3 + r'][ci][co] = w[co][ci][2-r'][2-s']            (dgrad = conv of dy with the rotated kernel)
+__global__ void pack_conv3_kernel(const float* __restrict__ w, int cout, int cin, __nv_bfloat16* __restrict__ wf,
+                                  __nv_bfloat16* __restrict__ wd) {
+  const size_t total = (size_t)cout * cin * 9;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = i % 3, r = (i / 3) % 3;
+    const int ci = (i / 9) % cin;
+    const int co = i / (9 * (size_t)cin);
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+    if (wf) wf[((size_t)(s * 3 + r) * cout + co) * cin + ci] = v;
+    if (wd) wd[((size_t)((2 - s) * 3 + (2 - r)) * cin + ci) * cout + co] = v;
+  }
+}
+// torch ConvTranspose2d weight (Cin, Cout, 2, 2) fp32 ->
+//   wf[(r*2+s)*Cout + co][ci]     (fprop: GEMM N = 4*Cout)
+//   wd[ci][(r*2+s)*Cout + co]     (dgrad: GEMM K = 4*Cout)
+__global__ void pack_convT_kernel(const float* __restrict__ w, int cin, int cout, __nv_bfloat16* __restrict__ wf,
+                                  __nv_bfloat16* __restrict__ wd) {
+  const size_t total = (size_t)cin * cout * 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int rs = i % 4;
+    const int co = (i / 4) % cout;
+    const int ci = i / (4 * (size_t)cout);
+    const __nv_bfloat16 v = __float2bfloat16_rn(w[i]);
+    if (wf) wf[((size_t)rs * cout + co) * cin + ci] = v;
+    if (wd) wd[(size_t)ci * 4 * cout + (size_t)rs * cout + co] = v;
+  }
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n) {
+  const size_t n4 = n / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    uint2 o;
+    *reinterpret_cast<__nv_bfloat162*>(&o.x) = __floats2bfloat162_rn(v.x, v.y);
+    *reinterpret_cast<__nv_bfloat162*>(&o.y) = __floats2bfloat162_rn(v.z, v.w);
+    reinterpret_cast<uint2*>(y)[i] = o;
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+
+// ---------------------------------------------------------------------------------- first conv (Cin = 1)
+// y[n,h,w,co] = sum_{r,s} w[co][r][s] * (x[n,h+r-1,w+s-1] * (1 - mask0[h+r-1,w+s-1]))     (Q1: image-0 mask)
+// 8 threads per pixel, 8 channels each (Cout = 64).  Per-channel sum / sum-of-squares are accumulated in registers
+// over a grid-stride loop and reduced per block -> stats_partial[block][2][64].
+constexpr int kC1Cout = 64;
+__global__ void __launch_bounds__(256) conv_c1_fprop_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask0,
+                                                            const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
+                                                            float* __restrict__ stats_partial, int N, int H, int W) {
+  __shared__ float sw[kC1Cout * 9];
+  __shared__ float sred[2][kC1Cout];
+  for (int i = threadIdx.x; i < kC1Cout * 9; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 2 * kC1Cout; i += blockDim.x) (&sred[0][0])[i] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x & 7;  // channel group: channels cg*8 .. cg*8+7
+  float wr[8][9];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[c][t] = sw[(cg * 8 + c) * 9 + t];
+  float s1[8], s2[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s1[c] = s2[c] = 0.f;
+  const size_t npix = (size_t)N * H * W;
+  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < npix;
+       pix += ((size_t)gridDim.x * blockDim.x) >> 3) {
+    const int wq = pix % W;
+    const int hq = (pix / W) % H;
+    const size_t nb = pix / ((size_t)W * H);
+    float xin[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int hh = hq + r - 1, ww = wq + s - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+          v = __ldg(x + (nb * H + hh) * W + ww);
+          if (mask0 != nullptr && mask0[hh * W + ww]) v = 0.f;
+        }
+        xin[r * 3 + s] = v;
+      }
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float a = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) a = fmaf(wr[c][t], xin[t], a);
+      o[c] = a;
+      s1[c] += a;
+      s2[c] += a * a;
+    }
+    reinterpret_cast<uint4*>(y)[pix * 8 + cg] = pack8(o);
+  }
+  if (stats_partial != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      // lanes with equal cg: xor-reduce over lane bits 3,4
+      float a = s1[c], b = s2[c];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      b += __shfl_xor_sync(0xffffffffu, b, 8);
+      b += __shfl_xor_sync(0xffffffffu, b, 16);
+      if ((threadIdx.x & 31) < 8) {
+        atomicAdd(&sred[0][cg * 8 + c], a);
+        atomicAdd(&sred[1][cg * 8 + c], b);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * kC1Cout; i += blockDim.x)
+      stats_partial[(size_t)blockIdx.x * 2 * kC1Cout + i] = (&sred[0][0])[i];
+  }
+}
+
+// dW[co][r][s] = sum_p dy[p,co] * xm[p + (r-1, s-1)]; partial[block][64*9], reduced by a second tiny kernel.
+__global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask0,
+                                                            const __nv_bfloat16* __restrict__ dy, float* __restrict__ partial,
+                                                            int N, int H, int W) {
+  __shared__ float sred[kC1Cout * 9];
+  for (int i = threadIdx.x; i < kC1Cout * 9; i += blockDim.x) sred[i] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x & 7;
+  float acc[8][9];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
+  const size_t npix = (size_t)N * H * W;
+  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < npix;
+       pix += ((size_t)gridDim.x * blockDim.x) >> 3) {
+    const int wq = pix % W;
+    const int hq = (pix / W) % H;
+    const size_t nb = pix / ((size_t)W * H);
+    float xin[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int hh = hq + r - 1, ww = wq + s - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+          v = __ldg(x + (nb * H + hh) * W + ww);
+          if (mask0 != nullptr && mask0[hh * W + ww]) v = 0.f;
+        }
+        xin[r * 3 + s] = v;
+      }
+    float g[8];
+    unpack8(reinterpret_cast<const uint4*>(dy)[pix * 8 + cg], g);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], xin[t], acc[c][t]);
+  }
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float a = acc[c][t];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      if ((threadIdx.x & 31) < 8) atomicAdd(&sred[(cg * 8 + c) * 9 + t], a);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kC1Cout * 9; i += blockDim.x) partial[(size_t)blockIdx.x * kC1Cout * 9 + i] = sred[i];
+}
+__global__ void reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out, int rows, int cols,
+                                   int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  double a = 0.0;
+  for (int r = 0; r < rows; ++r) a += partial[(size_t)r * cols + c];
+  out[c] = accumulate ? out[c] + (float)a : (float)a;
+}
+
+// ---------------------------------------------------------------------------------- BN finalize
+// partial layout: [grid][2][bn_tile]; the CTA with index b owns channel tile (b % n_tiles).
+// Train: mean/var from the batch (biased var for normalisation, unbiased for running_var); the conv bias is not
+// applied in the data path (it cancels inside train-mode BN) but it shifts the batch mean that running_mean tracks.
+// Eval: scale/shift from the running statistics (bias folded into the shift).
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int grid, int bn_tile, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ conv_bias, float* running_mean, float* running_var,
+                                   float momentum, float eps, int training, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  const float cb = conv_bias ? conv_bias[c] : 0.f;
+  float mean, rstd;
+  if (training) {
+    const int n_tiles = C / bn_tile;
+    const int nt = c / bn_tile, j = c % bn_tile;
+    double s1 = 0.0, s2 = 0.0;
+    for (int b = nt; b < grid; b += n_tiles) {
+      s1 += partial[((size_t)b * 2 + 0) * bn_tile + j];
+      s2 += partial[((size_t)b * 2 + 1) * bn_tile + j];
+    }
+    const double m = s1 / count;
+    double var = s2 / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (mean + cb);
+      const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+  } else {
+    mean = running_mean[c] - cb;   // data path carries y without the conv bias
+    rstd = rsqrtf(running_var[c] + eps);
+  }
+  scale[c] = g * rstd;
+  shift[c] = bt - mean * g * rstd;
+  if (mean_out) mean_out[c] = mean;
+  if (rstd_out) rstd_out[c] = rstd;
+}
+
+// ---------------------------------------------------------------------------------- BN apply + ReLU (+ pool)
+__global__ void __launch_bounds__(256) bn_relu_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ a,
+                                                      size_t npix, int C) {
+  const int cgs = C >> 3;
+  const size_t total = npix * cgs;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cg = i % cgs;
+    float f[8], sc[8], sh[8];
+    unpack8(reinterpret_cast<const uint4*>(y)[i], f);
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale) + cg * 2);
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale) + cg * 2 + 1);
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift) + cg * 2);
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift) + cg * 2 + 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+    reinterpret_cast<uint4*>(a)[i] = pack8(f);
+  }
+}
+// one thread: a 2x2 pixel quad x 8 channels -> 4 activated vectors + 1 pooled vector
+__global__ void __launch_bounds__(256) bn_relu_pool_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, __nv_bfloat16* __restrict__ a,
+                                                           __nv_bfloat16* __restrict__ pooled, int N, int H, int W, int C) {
+  const int cgs = C >> 3;
+  const int Hp = H >> 1, Wp = W >> 1;
+  const size_t total = (size_t)N * Hp * Wp * cgs;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cg = i % cgs;
+    const size_t q = i / cgs;
+    const int wp = q % Wp;
+    const int hp = (q / Wp) % Hp;
+    const size_t nb = q / ((size_t)Wp * Hp);
+    float sc[8], sh[8], mx[8];
+    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale) + cg * 2);
+    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale) + cg * 2 + 1);
+    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift) + cg * 2);
+    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift) + cg * 2 + 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx[k] = 0.f;  // ReLU outputs are >= 0
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+      const size_t pix = (nb * H + (hp * 2 + (d >> 1))) * W + (wp * 2 + (d & 1));
+      float f[8];
+      unpack8(reinterpret_cast<const uint4*>(y)[pix * cgs + cg], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+      }
+      const uint4 pk = pack8(f);
+      reinterpret_cast<uint4*>(a)[pix * cgs + cg] = pk;
+      float fr[8];
+      unpack8(pk, fr);  // pool the bf16-rounded values (what consumers of `a` see)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mx[k] = fmaxf(mx[k], fr[k]);
+    }
+    reinterpret_cast<uint4*>(pooled)[q * cgs + cg] = pack8(mx);
+  }
+}
+
+// ---------------------------------------------------------------------------------- BN/ReLU/pool backward
+// g  = da (+ dpool routed to the first maximum of its 2x2 window, ATen max_pool2d semantics)
+// dz = g * [z > 0],  z = y*scale + shift,  xhat = (y - mean) * rstd
+// pass 1: per-channel sum(dz), sum(dz * xhat)  -> partial[block][2][C]
+// pass 2: dy = scale * (dz - sum_dz/n - xhat * sum_dzx/n)
+template <bool kPool, bool kApply>
+__global__ void __launch_bounds__(256) bn_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ dpool,
+                                                     const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                                     const float* __restrict__ shift, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const float* __restrict__ sums,
+                                                     float inv_count, float* __restrict__ partial,
+                                                     __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C) {
+  extern __shared__ float sacc[];  // [2][C] (reduce pass)
+  const int cgs = C >> 3;
+  if (!kApply) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
+    __syncthreads();
+  }
+  // a block handles a fixed channel group per thread: threads are laid out [pixel-slot][cg] with cg fastest
+  const int tpb = blockDim.x;
+  const int slots = tpb / cgs > 0 ? tpb / cgs : 1;
+  const int cg = threadIdx.x % cgs;
+  const int slot = threadIdx.x / cgs;
+  const bool active = slot < slots && cgs <= tpb;
+  float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8];
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = scale[cg * 8 + k];
+      sh[k] = shift[cg * 8 + k];
+      mu[k] = mean[cg * 8 + k];
+      rs[k] = rstd[cg * 8 + k];
+      if (kApply) {
+        k1[k] = sums[cg * 8 + k] * inv_count;
+        k2[k] = sums[C + cg * 8 + k] * inv_count;
+      }
+    }
+  }
+  float a1[8], a2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a1[k] = a2[k] = 0.f;
+  const int Hq = kPool ? H >> 1 : H, Wq = kPool ? W >> 1 : W;
+  const size_t units = (size_t)N * Hq * Wq;  // quads (pool) or pixels
+  if (active) {
+    for (size_t u = (size_t)blockIdx.x * slots + slot; u < units; u += (size_t)gridDim.x * slots) {
+      if (kPool) {
+        const int wp = u % Wq;
+        const int hp = (u / Wq) % Hq;
+        const size_t nb = u / ((size_t)Wq * Hq);
+        float gp[8];
+        unpack8(reinterpret_cast<const uint4*>(dpool)[u * cgs + cg], gp);
+        float yv[4][8], z[4][8];
+        size_t pixs[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          pixs[d] = (nb * H + (hp * 2 + (d >> 1))) * W + (wp * 2 + (d & 1));
+          unpack8(reinterpret_cast<const uint4*>(y)[pixs[d] * cgs + cg], yv[d]);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            // compare the bf16-rounded activations, exactly what the forward pooled
+            z[d][k] = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(yv[d][k], sc[k], sh[k]), 0.f)));
+          }
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          float g[8];
+          if (da != nullptr) unpack8(reinterpret_cast<const uint4*>(da)[pixs[d] * cgs + cg], g);
+          else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g[k] = 0.f;
+          }
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            // first maximum in row-major window order
+            bool is_max = true;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (e < d) is_max = is_max && (z[d][k] > z[e][k]);
+              if (e > d) is_max = is_max && (z[d][k] >= z[e][k]);
+            }
+            const float gg = g[k] + (is_max ? gp[k] : 0.f);
+            const float dz = (z[d][k] > 0.f) ? gg : 0.f;
+            const float xh = (yv[d][k] - mu[k]) * rs[k];
+            if (kApply) o[k] = sc[k] * (dz - k1[k] - xh * k2[k]);
+            else { a1[k] += dz; a2[k] += dz * xh; }
+          }
+          if (kApply) reinterpret_cast<uint4*>(dy)[pixs[d] * cgs + cg] = pack8(o);
+        }
+      } else {
+        float yv[8], g[8], o[8];
+        unpack8(reinterpret_cast<const uint4*>(y)[u * cgs + cg], yv);
+        unpack8(reinterpret_cast<const uint4*>(da)[u * cgs + cg], g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float z = fmaf(yv[k], sc[k], sh[k]);
+          const float dz = (z > 0.f) ? g[k] : 0.f;
+          const float xh = (yv[k] - mu[k]) * rs[k];
+          if (kApply) o[k] = sc[k] * (dz - k1[k] - xh * k2[k]);
+          else { a1[k] += dz; a2[k] += dz * xh; }
+        }
+        if (kApply) reinterpret_cast<uint4*>(dy)[u * cgs + cg] = pack8(o);
+      }
+    }
+  }
+  if (!kApply) {
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        atomicAdd(&sacc[cg * 8 + k], a1[k]);
+        atomicAdd(&sacc[C + cg * 8 + k], a2[k]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) partial[(size_t)blockIdx.x * 2 * C + i] = sacc[i];
+  }
+}
+
+// per-channel sums of a bf16 (rows, C) tensor -> partial[block][C]   (ConvTranspose2d bias gradient)
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, size_t rows, int C,
+                                                          float* __restrict__ partial) {
+  extern __shared__ float sacc[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cgs = C >> 3;
+  const int slots = blockDim.x / cgs;
+  const int cg = threadIdx.x % cgs, slot = threadIdx.x / cgs;
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.f;
+  if (slot < slots) {
+    for (size_t r = (size_t)blockIdx.x * slots + slot; r < rows; r += (size_t)gridDim.x * slots) {
+      float f[8];
+      unpack8(reinterpret_cast<const uint4*>(x)[r * cgs + cg], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += f[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&sacc[cg * 8 + k], a[k]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) partial[(size_t)blockIdx.x * C + i] = sacc[i];
+}
+
+static int ew_grid(size_t work_items, int threads, int per_sm = 8) {
+  size_t blocks = (work_items + threads - 1) / threads;
+  const size_t cap = (size_t)num_sms() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace cmu
+
+using namespace cmu;
+
+extern "C" {
+
+int cmu_pack_conv3x3_weights(const float* w, int cout, int cin, void* wf, void* wd, void* stream) {
+  const size_t total = (size_t)cout * cin * 9;
+  pack_conv3_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(w, cout, cin, (__nv_bfloat16*)wf,
+                                                                          (__nv_bfloat16*)wd);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_pack_convT2x2_weights(const float* w, int cin, int cout, void* wf, void* wd, void* stream) {
+  const size_t total = (size_t)cout * cin * 4;
+  pack_convT_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(w, cin, cout, (__nv_bfloat16*)wf,
+                                                                          (__nv_bfloat16*)wd);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream) {
+  CMU_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0,
+              "cast: pointers must be 16/8-byte aligned");
+  cast_bf16_kernel<<<ew_grid((size_t)n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, (size_t)n);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_conv3x3_c1_grid(void) { return num_sms() * 4; }
+
+int cmu_conv3x3_c1_fprop(const float* x, const unsigned char* mask0, const float* w, int cout, void* y,
+                         float* stats_partial, int n, int h, int wd, void* stream) {
+  CMU_REQUIRE(cout == kC1Cout, "conv3x3_c1: Cout must be 64 (got %d)", cout);
+  conv_c1_fprop_kernel<<<cmu_conv3x3_c1_grid(), 256, 0, (cudaStream_t)stream>>>(x, mask0, w, (__nv_bfloat16*)y,
+                                                                               stats_partial, n, h, wd);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_conv3x3_c1_wgrad(const float* x, const unsigned char* mask0, const void* dy, int cout, float* partial, float* dw,
+                         int accumulate, int n, int h, int wd, void* stream) {
+  CMU_REQUIRE(cout == kC1Cout, "conv3x3_c1: Cout must be 64 (got %d)", cout);
+  const int grid = cmu_conv3x3_c1_grid();
+  conv_c1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, mask0, (const __nv_bfloat16*)dy, partial, n, h, wd);
+  CMU_LAUNCH_CHECK();
+  reduce_rows_kernel<<<ceil_div(kC1Cout * 9, 128), 128, 0, (cudaStream_t)stream>>>(partial, dw, grid, kC1Cout * 9,
+                                                                                   accumulate);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_bn_finalize(const float* partial, int grid, int bn_tile, int c, double count, const float* gamma,
+                    const float* beta, const float* conv_bias, float* running_mean, float* running_var, float momentum,
+                    float eps, int training, float* scale, float* shift, float* mean, float* rstd, void* stream) {
+  CMU_REQUIRE(!training || (partial != nullptr && grid > 0 && bn_tile > 0 && c % bn_tile == 0), "bn_finalize: bad partial layout");
+  CMU_REQUIRE(training || (running_mean && running_var), "bn_finalize: eval mode needs running statistics");
+  bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(partial, grid, bn_tile, c, count, gamma, beta,
+                                                                        conv_bias, running_mean, running_var, momentum,
+                                                                        eps, training, scale, shift, mean, rstd);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_bn_relu_apply(const void* y, const float* scale, const float* shift, void* a, void* pooled, int n, int h, int w,
+                      int c, void* stream) {
+  CMU_REQUIRE(c % 8 == 0, "bn_relu_apply: C must be a multiple of 8");
+  if (pooled != nullptr) {
+    CMU_REQUIRE(h % 2 == 0 && w % 2 == 0, "bn_relu_apply: pooling needs even H, W");
+    const size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 8);
+    bn_relu_pool_kernel<<<ew_grid(total, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)y, scale, shift, (__nv_bfloat16*)a, (__nv_bfloat16*)pooled, n, h, w, c);
+  } else {
+    const size_t npix = (size_t)n * h * w;
+    bn_relu_kernel<<<ew_grid(npix * (c / 8), 256, 16), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)y, scale, shift, (__nv_bfloat16*)a, npix, c);
+  }
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_colsum_bf16(const void* x, long long rows, int c, float* partial, float* out, void* stream) {
+  CMU_REQUIRE(c % 8 == 0 && c / 8 <= 256, "colsum_bf16: C must be a multiple of 8 and <= 2048");
+  const int grid = cmu_bn_bwd_grid();
+  colsum_bf16_kernel<<<grid, 256, c * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (size_t)rows, c,
+                                                                            partial);
+  CMU_LAUNCH_CHECK();
+  reduce_rows_kernel<<<ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(partial, out, grid, c, 0);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_bn_bwd_grid(void) { return num_sms() * 4; }
+
+// sums: [2][C] device buffer receiving (sum dz, sum dz*xhat) == (dbeta, dgamma); partial: [cmu_bn_bwd_grid()][2][C]
+int cmu_bn_relu_bwd(const void* da, const void* dpool, const void* y, const float* scale, const float* shift,
+                    const float* mean, const float* rstd, float* partial, float* sums, void* dy, int n, int h, int w,
+                    int c, void* stream) {
+  CMU_REQUIRE(c % 8 == 0 && c / 8 <= 256, "bn_relu_bwd: C must be a multiple of 8 and <= 2048");
+  CMU_REQUIRE(da != nullptr || dpool != nullptr, "bn_relu_bwd: no incoming gradient");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = cmu_bn_bwd_grid();
+  const size_t shmem = 2 * (size_t)c * sizeof(float);
+  const float inv_count = 1.f / ((float)n * h * w);
+  const __nv_bfloat16 *pda = (const __nv_bfloat16*)da, *pdp = (const __nv_bfloat16*)dpool, *py = (const __nv_bfloat16*)y;
+  if (dpool != nullptr) {
+    CMU_REQUIRE(h % 2 == 0 && w % 2 == 0, "bn_relu_bwd: pooling needs even H, W");
+    bn_bwd_kernel<true, false><<<grid, 256, shmem, st>>>(pda, pdp, py, scale, shift, mean, rstd, nullptr, inv_count,
+                                                         partial, nullptr, n, h, w, c);
+  } else {
+    bn_bwd_kernel<false, false><<<grid, 256, shmem, st>>>(pda, pdp, py, scale, shift, mean, rstd, nullptr, inv_count,
+                                                          partial, nullptr, n, h, w, c);
+  }
+  CMU_LAUNCH_CHECK();
+  reduce_rows_kernel<<<ceil_div(2 * c, 128), 128, 0, st>>>(partial, sums, grid, 2 * c, 0);
+  CMU_LAUNCH_CHECK();
+  if (dpool != nullptr)
+    bn_bwd_kernel<true, true><<<grid * 4, 256, 0, st>>>(pda, pdp, py, scale, shift, mean, rstd, sums, inv_count, nullptr,
+                                                        (__nv_bfloat16*)dy, n, h, w, c);
+  else
+    bn_bwd_kernel<false, true><<<grid * 4, 256, 0, st>>>(pda, pdp, py, scale, shift, mean, rstd, sums, inv_count,
+                                                         nullptr, (__nv_bfloat16*)dy, n, h, w, c);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,501 @@
+// Loss / head kernels (HBM- or latency-bound): 1x1 output head (64 -> 2), masked-pixel MSE with the per-row target
+// normalisation, fused L2-normalise + logits + online-softmax cross-entropy (InfoNCE) with its gradient, and the
+// fine-tuning Dice / IoU / soft-target cross-entropy reductions.  Warp-shuffle reductions, one atomic per block.
+#include "common.cuh"
+#include "../../include/cmu_b200.h"
+
+namespace cmu {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ 1x1 head
+// a: (npix, 64) bf16 NHWC (post BN+ReLU);  out: (N, 2, H, W) fp32 NCHW;  w: (2, 64) fp32, b: (2)
+// 8 lanes per pixel (16 bytes each) -> fully coalesced 128-byte rows.
+__global__ void __launch_bounds__(256) head1x1_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float* __restrict__ out,
+                                                          size_t npix, size_t hw) {
+  const int cg = threadIdx.x & 7;
+  float w0[8], w1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    w0[k] = w[cg * 8 + k];
+    w1[k] = w[64 + cg * 8 + k];
+  }
+  const float b0 = b[0], b1 = b[1];
+  const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 3;
+  const size_t npad = (npix + 3) & ~size_t(3);   // keep whole warps in the loop for the shuffles
+  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < npad; pix += stride) {
+    float f[8];
+    float d0 = 0.f, d1 = 0.f;
+    if (pix < npix) {
+      unpack8f(reinterpret_cast<const uint4*>(a)[pix * 8 + cg], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        d0 = fmaf(f[k], w0[k], d0);
+        d1 = fmaf(f[k], w1[k], d1);
+      }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+    }
+    if (cg == 0 && pix < npix) {
+      const size_t n = pix / hw, p = pix % hw;
+      out[(n * 2 + 0) * hw + p] = d0 + b0;
+      out[(n * 2 + 1) * hw + p] = d1 + b1;
+    }
+  }
+}
+// dout: (N,2,H,W) fp32.  da[p,k] = d0*w0[k] + d1*w1[k] (bf16 NHWC);  dw[c][k] += sum_p d_c[p]*a[p,k];  db[c] += sum d_c
+// acc: float[130] = dw (2*64) followed by db (2); must be zero-initialised by the caller.
+__global__ void __launch_bounds__(256) head1x1_bwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ w,
+                                                          const float* __restrict__ dout, __nv_bfloat16* __restrict__ da,
+                                                          float* __restrict__ acc, size_t npix, size_t hw) {
+  __shared__ float sacc[130];
+  for (int i = threadIdx.x; i < 130; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x & 7;
+  float w0[8], w1[8], g0[8], g1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    w0[k] = w[cg * 8 + k];
+    w1[k] = w[64 + cg * 8 + k];
+    g0[k] = g1[k] = 0.f;
+  }
+  float s0 = 0.f, s1 = 0.f;
+  const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 3;
+  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < npix; pix += stride) {
+    const size_t n = pix / hw, p = pix % hw;
+    const float d0 = __ldg(dout + (n * 2 + 0) * hw + p);
+    const float d1 = __ldg(dout + (n * 2 + 1) * hw + p);
+    float f[8], o[8];
+    unpack8f(reinterpret_cast<const uint4*>(a)[pix * 8 + cg], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      o[k] = d0 * w0[k] + d1 * w1[k];
+      g0[k] = fmaf(d0, f[k], g0[k]);
+      g1[k] = fmaf(d1, f[k], g1[k]);
+    }
+    uint4 pk;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
+    reinterpret_cast<uint4*>(da)[pix * 8 + cg] = pk;
+    if (cg == 0) {
+      s0 += d0;
+      s1 += d1;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float x0 = g0[k], x1 = g1[k];
+    x0 += __shfl_xor_sync(0xffffffffu, x0, 8);
+    x0 += __shfl_xor_sync(0xffffffffu, x0, 16);
+    x1 += __shfl_xor_sync(0xffffffffu, x1, 8);
+    x1 += __shfl_xor_sync(0xffffffffu, x1, 16);
+    if ((threadIdx.x & 31) < 8) {
+      atomicAdd(&sacc[cg * 8 + k], x0);
+      atomicAdd(&sacc[64 + cg * 8 + k], x1);
+    }
+  }
+  s0 = warp_sum(s0);
+  s1 = warp_sum(s1);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sacc[128], s0);
+    atomicAdd(&sacc[129], s1);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 130; i += blockDim.x) atomicAdd(&acc[i], sacc[i]);
+}
+
+// ------------------------------------------------------------------------------------------ masked MSE
+// cmunet_head.py:62-70.  One warp per image row (b,h): t = (x - mean_w) / sqrt(var_w_unbiased + 1e-6);
+// acc[0] += sum m*(p-t)^2, acc[1] += sum m.   pred is addressed as pred + b*pred_bstride + h*W + w (channel-1 view).
+template <bool kBwd>
+__global__ void __launch_bounds__(256) masked_mse_kernel(const float* __restrict__ x, const float* __restrict__ pred,
+                                                         long long pred_bstride, const uint8_t* __restrict__ mask,
+                                                         double* __restrict__ acc, float* __restrict__ dpred,
+                                                         long long dpred_bstride, const float* __restrict__ gscale, int B,
+                                                         int H, int W) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const size_t rows = (size_t)B * H;
+  double num = 0.0, den = 0.0;
+  float coef = 0.f;
+  if (kBwd) coef = gscale[0] * 2.f / (float)acc[1];   // rc_weight * upstream grad * 2 / sum(mask)
+  for (size_t row = (size_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
+       row += (size_t)gridDim.x * warps_per_block) {
+    const size_t b = row / H, h = row % H;
+    const float* xr = x + row * W;
+    float s = 0.f;
+    for (int w = lane; w < W; w += 32) s += xr[w];
+    const float mean = warp_sum(s) / (float)W;
+    float v = 0.f;
+    for (int w = lane; w < W; w += 32) {
+      const float d = xr[w] - mean;
+      v += d * d;
+    }
+    const float var = warp_sum(v) / (float)(W - 1);
+    const float inv = rsqrtf(var + 1e-6f);
+    const float* pr = pred + b * pred_bstride + h * W;
+    const uint8_t* mr = mask + row * W;
+    float ln = 0.f, ld = 0.f;
+    for (int w = lane; w < W; w += 32) {
+      const float t = (xr[w] - mean) * inv;
+      const float m = (float)mr[w];
+      const float d = pr[w] - t;
+      if (kBwd) dpred[b * dpred_bstride + h * W + w] = coef * m * d;
+      else {
+        ln += m * d * d;
+        ld += m;
+      }
+    }
+    if (!kBwd) {
+      num += (double)warp_sum(ln);
+      den += (double)warp_sum(ld);
+    }
+  }
+  if (!kBwd) {
+    __shared__ double sn[8], sd[8];
+    if (lane == 0) {
+      sn[threadIdx.x >> 5] = num;
+      sd[threadIdx.x >> 5] = den;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0, c = 0;
+      for (int i = 0; i < warps_per_block; ++i) {
+        a += sn[i];
+        c += sd[i];
+      }
+      atomicAdd(&acc[0], a);
+      atomicAdd(&acc[1], c);
+    }
+  }
+}
+__global__ void masked_mse_finish_kernel(const double* acc, float rc_weight, float* loss) {
+  loss[0] = rc_weight * (float)(acc[0] / acc[1]);
+}
+
+// ------------------------------------------------------------------------------------------ InfoNCE
+// cmunet_head.py:74-88.  One block per query row i:
+//   p = q_i / max(|q_i|, 1e-12);  s_j = <p, z_j> / tau  (z rows already L2-normalised, all-gathered);
+//   loss_i = logsumexp_j s_j - s_label,  label = i + label_offset;
+//   dq_i = (I - p p^T)/|q_i| * [ sum_j (softmax_j - onehot_j) z_j ] * coef / tau,  coef = ct_weight*2*tau/B
+// The logits never leave the block (online softmax over column chunks); loss_rows[i] and dq are outputs.
+constexpr int kNceDim = 256;
+__global__ void __launch_bounds__(256) infonce_kernel(const float* __restrict__ q, const float* __restrict__ z, int n_keys,
+                                                      int label_offset, float inv_tau, float coef,
+                                                      float* __restrict__ loss_rows, float* __restrict__ dq) {
+  __shared__ float sp[kNceDim];
+  __shared__ float sred[8];
+  __shared__ float s_m, s_l;
+  extern __shared__ float slog[];  // [n_keys] logits of this row
+  const int i = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float qv = q[(size_t)i * kNceDim + tid];
+  float ss = warp_sum(qv * qv);
+  if (lane == 0) sred[wid] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int k = 0; k < 8; ++k) tot += sred[k];
+  const float nrm = fmaxf(sqrtf(tot), 1e-12f);
+  sp[tid] = qv / nrm;
+  __syncthreads();
+  // logits: one warp per key, lanes stride the 256-dim dot product (coalesced reads of z rows)
+  for (int j = wid; j < n_keys; j += 8) {
+    const float* zr = z + (size_t)j * kNceDim;
+    float d = 0.f;
+#pragma unroll
+    for (int k = 0; k < kNceDim / 32; ++k) d = fmaf(sp[lane + 32 * k], zr[lane + 32 * k], d);
+    d = warp_sum(d);
+    if (lane == 0) slog[j] = d * inv_tau;
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int j = tid; j < n_keys; j += 256) m = fmaxf(m, slog[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __syncthreads();
+  if (lane == 0) sred[wid] = m;
+  __syncthreads();
+  m = sred[0];
+  for (int k = 1; k < 8; ++k) m = fmaxf(m, sred[k]);
+  float l = 0.f;
+  for (int j = tid; j < n_keys; j += 256) l += __expf(slog[j] - m);
+  l = warp_sum(l);
+  __syncthreads();
+  if (lane == 0) sred[wid] = l;
+  __syncthreads();
+  l = 0.f;
+  for (int k = 0; k < 8; ++k) l += sred[k];
+  const int label = i + label_offset;
+  if (tid == 0) {
+    loss_rows[i] = (m + logf(l)) - slog[label];
+    s_m = m;
+    s_l = l;
+  }
+  __syncthreads();
+  if (dq != nullptr) {
+    // g[d] = sum_j (softmax_j - onehot_j) z[j][d]; thread tid owns dimension d = tid (coalesced over j rows)
+    float g = 0.f;
+    const float invl = 1.f / s_l;
+    for (int j = 0; j < n_keys; ++j) {
+      float wj = __expf(slog[j] - s_m) * invl;
+      if (j == label) wj -= 1.f;
+      g = fmaf(wj, z[(size_t)j * kNceDim + tid], g);
+    }
+    g *= coef * inv_tau;
+    // through the normalisation: dq = (g - p <p, g>) / |q|
+    float pg = warp_sum(sp[tid] * g);
+    __syncthreads();
+    if (lane == 0) sred[wid] = pg;
+    __syncthreads();
+    pg = 0.f;
+    for (int k = 0; k < 8; ++k) pg += sred[k];
+    dq[(size_t)i * kNceDim + tid] = (g - sp[tid] * pg) / nrm;
+  }
+}
+__global__ void mean_scale_kernel(const float* __restrict__ rows, int n, float scale, float* __restrict__ out) {
+  // deterministic single-warp mean
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 32) s += rows[i];
+  s = warp_sum(s);
+  if (threadIdx.x == 0) out[0] = scale * s / (float)n;
+}
+__global__ void l2_normalize_rows_kernel(const float* __restrict__ x, float* __restrict__ y, int dim) {
+  __shared__ float sred[32];
+  const float* xr = x + (size_t)blockIdx.x * dim;
+  float s = 0.f;
+  for (int k = threadIdx.x; k < dim; k += blockDim.x) s += xr[k] * xr[k];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float tot = 0.f;
+  for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += sred[k];
+  const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+  for (int k = threadIdx.x; k < dim; k += blockDim.x) y[(size_t)blockIdx.x * dim + k] = xr[k] * inv;
+}
+
+// ------------------------------------------------------------------------------------------ Dice / IoU / CE (fine-tune)
+// FT/metrics.py:135-220,503.  logits (N,2,H,W) fp32; gt (N,2,H,W) float64 one-hot/probabilities (Q7).
+// acc[0]=tp=sum gt1*pr1  acc[1]=sum pr1  acc[2]=sum gt1  acc[3]=sum_c -y_c*log_softmax_c ; pr1 = [logit1 > logit0]
+// (softmax_1 > 0.5 <=> logit1 > logit0).  Optional dlogits = (softmax * sum_c y_c - y) * gscale / (N*H*W).
+__global__ void __launch_bounds__(256) seg_losses_kernel(const float* __restrict__ logits, const double* __restrict__ gt,
+                                                         double* __restrict__ acc, float* __restrict__ dlogits,
+                                                         const float* __restrict__ gscale, size_t npix, size_t hw) {
+  double tp = 0, spr = 0, sgt = 0, ce = 0;
+  const float gs = (dlogits != nullptr) ? gscale[0] / (float)npix : 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / hw, p = i % hw;
+    const float l0 = logits[(n * 2) * hw + p], l1 = logits[(n * 2 + 1) * hw + p];
+    const double y0 = gt[(n * 2) * hw + p], y1 = gt[(n * 2 + 1) * hw + p];
+    const float mx = fmaxf(l0, l1);
+    const float e0 = expf(l0 - mx), e1 = expf(l1 - mx);
+    const float lse = mx + logf(e0 + e1);
+    const double pr1 = (l1 > l0) ? 1.0 : 0.0;
+    tp += y1 * pr1;
+    spr += pr1;
+    sgt += y1;
+    ce += -(y0 * (double)(l0 - lse) + y1 * (double)(l1 - lse));
+    if (dlogits != nullptr) {
+      const float inv = 1.f / (e0 + e1);
+      const float ys = (float)(y0 + y1);
+      dlogits[(n * 2) * hw + p] = (e0 * inv * ys - (float)y0) * gs;
+      dlogits[(n * 2 + 1) * hw + p] = (e1 * inv * ys - (float)y1) * gs;
+    }
+  }
+  __shared__ double sred[4][8];
+  tp = warp_sum_d(tp); spr = warp_sum_d(spr); sgt = warp_sum_d(sgt); ce = warp_sum_d(ce);
+  if ((threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    sred[0][w] = tp; sred[1][w] = spr; sred[2][w] = sgt; sred[3][w] = ce;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double a = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a += sred[threadIdx.x][k];
+    atomicAdd(&acc[threadIdx.x], a);
+  }
+}
+// out[0]=dice_loss out[1]=iou_loss out[2]=ce_loss   (float64, as the reference's float64 targets promote them)
+__global__ void seg_losses_finish_kernel(const double* acc, double npix, double dice_eps, double beta, double iou_eps,
+                                         double* out) {
+  const double tp = acc[0], fp = acc[1] - acc[0], fn = acc[2] - acc[0];
+  const double b2 = beta * beta;
+  out[0] = 1.0 - ((1.0 + b2) * tp + dice_eps) / ((1.0 + b2) * tp + b2 * fn + fp + dice_eps);
+  out[1] = 1.0 - (tp + iou_eps) / (acc[2] + acc[1] - tp + iou_eps);
+  out[2] = acc[3] / npix;
+}
+
+// ------------------------------------------------------------------------------------------ small layout helpers
+// mean over the 2 channels of (N,2,H,W) fp32 -> (N, H*W) bf16  (cmunet.py:126 feeding projector.fc0)
+__global__ void chmean2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n_img, size_t hw) {
+  const size_t total = n_img * hw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / hw, p = i % hw;
+    y[i] = __float2bfloat16_rn(0.5f * (x[(n * 2) * hw + p] + x[(n * 2 + 1) * hw + p]));
+  }
+}
+// d(N,2,H,W)[:,c] = 0.5 * dx(N,H*W)  (fp32 in, fp32 out), optionally accumulating
+__global__ void chmean2_bwd_kernel(const float* __restrict__ dx, float* __restrict__ dout, size_t n_img, size_t hw) {
+  const size_t total = n_img * hw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / hw, p = i % hw;
+    const float g = 0.5f * dx[i];
+    dout[(n * 2) * hw + p] = g;
+    dout[(n * 2 + 1) * hw + p] = g;
+  }
+}
+// (N, HW, C) bf16 -> (N, C, HW) bf16 through a 32x32 smem tile  (cmunet.py:130 flattens NCHW order)
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int hw, int c) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const size_t n = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int p = p0 + r, cc = c0 + threadIdx.x;
+    if (p < hw && cc < c) tile[r][threadIdx.x] = x[(n * hw + p) * c + cc];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int cc = c0 + r, p = p0 + threadIdx.x;
+    if (p < hw && cc < c) y[(n * c + cc) * hw + p] = tile[threadIdx.x][r];
+  }
+}
+
+static int grid_for(size_t items, int threads, int per_sm = 8) {
+  size_t b = (items + threads - 1) / threads;
+  const size_t cap = (size_t)num_sms() * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace cmu
+
+using namespace cmu;
+
+extern "C" {
+
+int cmu_head1x1_fprop(const void* a, const float* w, const float* b, float* out, int n, int h, int wd, int cin, int cout,
+                      void* stream) {
+  CMU_REQUIRE(cin == 64 && cout == 2, "head1x1: only 64 -> 2 is supported (got %d -> %d)", cin, cout);
+  const size_t npix = (size_t)n * h * wd;
+  head1x1_fwd_kernel<<<grid_for(npix * 8, 256, 16), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, w, b, out,
+                                                                                   npix, (size_t)h * wd);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+// acc: float[130], zeroed here; on return acc[0:128] = dW (2,64), acc[128:130] = db.
+int cmu_head1x1_bwd(const void* a, const float* w, const float* dout, void* da, float* acc, int n, int h, int wd, int cin,
+                    int cout, void* stream) {
+  CMU_REQUIRE(cin == 64 && cout == 2, "head1x1: only 64 -> 2 is supported (got %d -> %d)", cin, cout);
+  const size_t npix = (size_t)n * h * wd;
+  CMU_CHECK_CUDA(cudaMemsetAsync(acc, 0, 130 * sizeof(float), (cudaStream_t)stream));
+  head1x1_bwd_kernel<<<grid_for(npix * 8, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)a, w, dout, (__nv_bfloat16*)da, acc, npix, (size_t)h * wd);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+// acc: double[2] scratch (kept for the backward); loss: float[1]
+int cmu_masked_mse_fwd(const float* x, const float* pred, long long pred_bstride, const unsigned char* mask, double* acc,
+                       float rc_weight, float* loss, int b, int h, int w, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  CMU_REQUIRE(w >= 2, "masked_mse: W must be >= 2 (unbiased variance)");
+  CMU_CHECK_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+  masked_mse_kernel<false><<<grid_for((size_t)b * h * 32, 256, 8), 256, 0, st>>>(x, pred, pred_bstride, mask, acc, nullptr,
+                                                                               0, nullptr, b, h, w);
+  CMU_LAUNCH_CHECK();
+  masked_mse_finish_kernel<<<1, 1, 0, st>>>(acc, rc_weight, loss);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+// gscale: device float[1] = rc_weight * upstream gradient; dpred addressed like pred (channel-1 view of a (B,2,H,W) grad)
+int cmu_masked_mse_bwd(const float* x, const float* pred, long long pred_bstride, const unsigned char* mask,
+                       const double* acc, const float* gscale, float* dpred, long long dpred_bstride, int b, int h, int w,
+                       void* stream) {
+  masked_mse_kernel<true><<<grid_for((size_t)b * h * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      x, pred, pred_bstride, mask, const_cast<double*>(acc), dpred, dpred_bstride, gscale, b, h, w);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_l2_normalize_rows(const float* x, float* y, int rows, int dim, void* stream) {
+  l2_normalize_rows_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(x, y, dim);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+// q: (B,256) raw predictor output; z: (n_keys,256) L2-normalised keys; loss[0] = ct_weight*2*tau*mean_i CE_i;
+// dq (optional, (B,256)) = d loss / d q.  loss_rows: float[B] scratch.
+int cmu_infonce_fwd_bwd(const float* q, const float* z, int batch, int n_keys, int dim, int label_offset, float tau,
+                        float ct_weight, float* loss_rows, float* loss, float* dq, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  CMU_REQUIRE(dim == kNceDim, "infonce: embedding dim must be 256 (got %d)", dim);
+  CMU_REQUIRE(label_offset >= 0 && label_offset + batch <= n_keys, "infonce: labels out of range");
+  const size_t shmem = (size_t)n_keys * sizeof(float);
+  CMU_REQUIRE(shmem <= 160 * 1024, "infonce: %d keys exceed the in-smem logits row; use the queue kernel", n_keys);
+  if (shmem > 40 * 1024)
+    CMU_CHECK_CUDA(cudaFuncSetAttribute(infonce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+  const float coef = ct_weight * 2.f * tau / (float)batch;
+  infonce_kernel<<<batch, 256, shmem, st>>>(q, z, n_keys, label_offset, 1.f / tau, coef, loss_rows, dq);
+  CMU_LAUNCH_CHECK();
+  mean_scale_kernel<<<1, 32, 0, st>>>(loss_rows, batch, ct_weight * 2.f * tau, loss);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+// acc: double[4] scratch; out: double[3] = (dice_loss, iou_loss, ce_loss); dlogits optional (CE gradient * gscale[0])
+int cmu_seg_losses(const float* logits, const double* gt, double* acc, double* out, float* dlogits, const float* gscale,
+                   int n, int h, int w, double dice_eps, double beta, double iou_eps, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t npix = (size_t)n * h * w;
+  CMU_CHECK_CUDA(cudaMemsetAsync(acc, 0, 4 * sizeof(double), st));
+  seg_losses_kernel<<<grid_for(npix, 256, 8), 256, 0, st>>>(logits, gt, acc, dlogits, gscale, npix, (size_t)h * w);
+  CMU_LAUNCH_CHECK();
+  seg_losses_finish_kernel<<<1, 1, 0, st>>>(acc, (double)npix, dice_eps, beta, iou_eps, out);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_channel_mean2_bf16(const float* x, void* y, int n, long long hw, void* stream) {
+  chmean2_kernel<<<grid_for((size_t)n * hw, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, (size_t)n,
+                                                                                    (size_t)hw);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+int cmu_channel_mean2_bwd(const float* dx, float* dout, int n, long long hw, void* stream) {
+  chmean2_bwd_kernel<<<grid_for((size_t)n * hw, 256, 8), 256, 0, (cudaStream_t)stream>>>(dx, dout, (size_t)n, (size_t)hw);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+int cmu_nhwc_to_nchw_bf16(const void* x, void* y, int n, int hw, int c, void* stream) {
+  dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), block(32, 8);
+  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, c);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

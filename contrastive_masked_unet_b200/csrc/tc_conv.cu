@@ -1,0 +1,466 @@
+// K1: persistent, warp-specialised tcgen05 implicit-GEMM for NHWC bf16 activations (sm_100a).
+//
+//   D[pixels, n] = sum_{tap, k} A[pixel + tap_offset, k] * Wp[tap][n][k]        (fp32 accumulate in TMEM)
+//
+// One kernel covers: conv3x3 pad 1 fprop and dgrad (dgrad = fprop with rotated/transposed weights),
+// 1x1 / plain GEMM, ConvTranspose2d(k2,s2) fprop (GEMM + 2x2 scatter epilogue) and its dgrad (gathered A).
+//
+// Data movement: every operand tile is a TMA box with SWIZZLE_128B (64 bf16 channels = one 128-byte row per
+// pixel).  conv3x3 loads, per 64-channel K chunk, THREE horizontally shifted (TH+2) x TW haloed patches (one per
+// kernel column s); the three kernel rows r are then plain 1024B-aligned row offsets of the same patch in the
+// UMMA shared-memory descriptor, so 3 TMA loads feed 9 taps (zero padding = TMA out-of-bounds fill).
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
+// warps 2..5 = epilogue (TMEM -> regs -> [bias] -> [per-channel sum / sum-of-squares for BatchNorm] -> bf16 ->
+// swizzled smem -> TMA store).  Accumulators are double buffered in TMEM so the epilogue of tile i overlaps the
+// MMAs of tile i+1.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/cmu_b200.h"
+
+namespace cmu {
+
+enum { MODE_CONV3 = 0, MODE_PLAIN = 1, MODE_CONVT_FPROP = 2, MODE_CONVT_DGRAD = 3 };
+
+constexpr int kK1Threads = 192;
+constexpr int kAStageBytes = 20480;  // max haloed patch: (8+2) x 16 or (16+2) x 8 rows of 128 B
+constexpr int kStagingBytes = 16384; // one 128 x 64 bf16 output slab
+
+struct K1Params {
+  CUtensorMap tmA0, tmA1, tmB, tmO0, tmO1;
+  int mode;
+  int N, H, W;      // pixel space of GEMM-M (output pixels; for convT: the low-resolution grid)
+  int c0, c1;       // channels of A source 0 / 1 (concat along K)
+  int n_total;      // GEMM N
+  int oc0;          // channels of output 0 (dual-output split; convT fprop: Cout)
+  int TW, TH, tw_shift;
+  int tiles_w, tiles_h, m_tiles, n_tiles;
+  int kc;           // number of 64-wide K chunks per tap
+  const float* bias;
+  int bias_mod;
+  float* stats;     // [gridDim.x][2][BN] partial (sum, sum of squares) or nullptr
+};
+
+template <int BN>
+struct K1Cfg {
+  static constexpr int kBStage = 3 * BN * 128;
+  static constexpr int kStage = kAStageBytes + kBStage;
+  static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmem = kStages * kStage + kStagingBytes + 1024 /*align*/ + 1024 /*barriers+stats*/ + 2 * BN * 4;
+};
+
+template <int OFF>
+__device__ __forceinline__ void bfly(float (&v)[32], uint32_t lane) {
+  const bool up = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < OFF; ++i) {
+    const float send = up ? v[i] : v[i + OFF];
+    const float keep = up ? v[i + OFF] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+// After the call, lane L holds in v[0] the sum over the 32 lanes of their v[L].
+__device__ __forceinline__ void column_sums(float (&v)[32], uint32_t lane) {
+  bfly<16>(v, lane);
+  bfly<8>(v, lane);
+  bfly<4>(v, lane);
+  bfly<2>(v, lane);
+  bfly<1>(v, lane);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant__ K1Params p) {
+  using Cfg = K1Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint64_t* full_bar = bars;                      // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;      // [kStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_stats = reinterpret_cast<float*>(bars + 32);  // [2][BN]
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmO0);
+  }
+  for (int i = threadIdx.x; i < 2 * BN; i += kK1Threads) s_stats[i] = 0.f;
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tile schedule: this CTA owns one n-tile (so its BN statistics stay in one smem slot) and strides over m-tiles
+  const int nt = blockIdx.x % p.n_tiles;
+  const int mt0 = blockIdx.x / p.n_tiles;
+  const int mstride = gridDim.x / p.n_tiles;
+  const int n0 = nt * BN;
+  const int shifts = (p.mode == MODE_CONV3) ? 3 : 1;
+  const int kc = p.kc;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      const uint32_t a_bytes = (p.mode == MODE_CONV3) ? (p.TH + 2) * p.TW * 128 : 128 * 128;
+      const uint32_t b_total = (p.mode == MODE_CONV3) ? 3 * BN * 128 : BN * 128;
+      uint32_t it = 0;
+      for (int mt = mt0; mt < p.m_tiles; mt += mstride) {
+        const int img = mt / tiles_per_img;
+        const int rem = mt - img * tiles_per_img;
+        const int h0 = (rem / p.tiles_w) * p.TH;
+        const int w0 = (rem % p.tiles_w) * p.TW;
+        for (int c = 0; c < kc; ++c) {
+          for (int s = 0; s < shifts; ++s, ++it) {
+            const uint32_t st = it % Cfg::kStages;
+            const uint32_t ph = (it / Cfg::kStages) & 1;
+            mbar_wait(&empty_bar[st], ph ^ 1);
+            uint8_t* sA = stage_base + st * Cfg::kStage;
+            uint8_t* sB = sA + kAStageBytes;
+            mbar_arrive_expect_tx(&full_bar[st], a_bytes + b_total);
+            if (p.mode == MODE_CONVT_DGRAD) {
+              const int per = p.c0 >> 6;
+              const int rs = c / per;
+              const int cc = (c - rs * per) << 6;
+              tma_load_5d(sA, &p.tmA0, &full_bar[st], (rs & 1) * p.c0 + cc, w0, rs >> 1, h0, img);
+            } else {
+              const int k0 = c << 6;
+              const bool second = k0 >= p.c0;
+              const CUtensorMap* src = second ? &p.tmA1 : &p.tmA0;
+              const int cc = second ? k0 - p.c0 : k0;
+              if (p.mode == MODE_CONV3)
+                tma_load_4d(sA, src, &full_bar[st], cc, w0 + s - 1, h0 - 1, img);
+              else
+                tma_load_4d(sA, src, &full_bar[st], cc, w0, h0, img);
+            }
+            tma_load_3d(sB, &p.tmB, &full_bar[st], c << 6, n0, (p.mode == MODE_CONV3) ? 3 * s : 0);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      const int taps = (p.mode == MODE_CONV3) ? 3 : 1;
+      const uint32_t a_tap_stride = p.TW * 128;
+      uint32_t it = 0, tile_it = 0;
+      for (int mt = mt0; mt < p.m_tiles; mt += mstride, ++tile_it) {
+        const uint32_t acc = tile_it & 1;
+        const uint32_t aph = (tile_it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        const int nstages = kc * shifts;
+        for (int sidx = 0; sidx < nstages; ++sidx, ++it) {
+          const uint32_t st = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&full_bar[st], ph);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(stage_base + st * Cfg::kStage);
+          const uint32_t sB = sA + kAStageBytes;
+          for (int r = 0; r < taps; ++r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = umma_smem_desc(sA + r * a_tap_stride + k * 32, 16, 1024);
+              const uint64_t bd = umma_smem_desc(sB + r * (BN * 128) + k * 32, 16, 1024);
+              umma_bf16(d_tmem, ad, bd, idesc, (sidx | r | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[st]);  // smem slot reusable once these MMAs have read it
+        }
+        umma_commit(&tfull_bar[acc]);   // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const uint32_t q = warp & 3;  // TMEM lane quadrant this warp may access
+    const uint32_t row = q * 32 + lane;
+    const bool store_thread = (threadIdx.x == 64);
+    const int th = row >> p.tw_shift;
+    const int tw = row & (p.TW - 1);
+    uint32_t tile_it = 0;
+    for (int mt = mt0; mt < p.m_tiles; mt += mstride, ++tile_it) {
+      const int img = mt / tiles_per_img;
+      const int rem = mt - img * tiles_per_img;
+      const int h0 = (rem / p.tiles_w) * p.TH;
+      const int w0 = (rem % p.tiles_w) * p.TW;
+      const bool valid = (h0 + th < p.H) && (w0 + tw < p.W);
+      const uint32_t acc = tile_it & 1;
+      const uint32_t aph = (tile_it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int slab = 0; slab < BN / 64; ++slab) {
+        if (store_thread) tma_store_wait_read0();  // previous store has finished reading the staging buffer
+        named_bar_sync(1, 128);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int j = slab * 2 + half;
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + ((q * 32) << 16) + acc * BN + j * 32, raw);
+          tmem_ld_wait();
+          if (j == BN / 32 - 1) {  // last read of this accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+          }
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+          if (p.bias != nullptr) {
+            const int cb = (n0 + j * 32) % p.bias_mod;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + cb + i);
+          }
+          // bf16 pack + swizzled staging store (16-byte chunk index XOR (row & 7): TMA SWIZZLE_128B pattern)
+          uint8_t* rowp = staging + row * 128;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            uint4 pk;
+            pk.x = pack_bf16(v[k4 * 8 + 0], v[k4 * 8 + 1]);
+            pk.y = pack_bf16(v[k4 * 8 + 2], v[k4 * 8 + 3]);
+            pk.z = pack_bf16(v[k4 * 8 + 4], v[k4 * 8 + 5]);
+            pk.w = pack_bf16(v[k4 * 8 + 6], v[k4 * 8 + 7]);
+            const int chunk = (half * 4 + k4) ^ (row & 7);
+            *reinterpret_cast<uint4*>(rowp + chunk * 16) = pk;
+          }
+          if (p.stats != nullptr) {
+            float s1[32], s2[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float x = valid ? v[i] : 0.f;
+              s1[i] = x;
+              s2[i] = x * x;
+            }
+            column_sums(s1, lane);
+            column_sums(s2, lane);
+            atomicAdd(&s_stats[j * 32 + lane], s1[0]);
+            atomicAdd(&s_stats[BN + j * 32 + lane], s2[0]);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (store_thread) {
+          const int nch = n0 + slab * 64;
+          if (p.mode == MODE_CONVT_FPROP) {
+            const int rs = nch / p.oc0;
+            const int co = nch - rs * p.oc0;
+            tma_store_5d(&p.tmO0, staging, (rs & 1) * p.oc0 + co, w0, rs >> 1, h0, img);
+          } else if (nch < p.oc0) {
+            tma_store_4d(&p.tmO0, staging, nch, w0, h0, img);
+          } else {
+            tma_store_4d(&p.tmO1, staging, nch - p.oc0, w0, h0, img);
+          }
+          tma_store_commit();
+        }
+      }
+    }
+    if (store_thread) tma_store_wait_all0();
+    if (p.stats != nullptr) {
+      named_bar_sync(1, 128);
+      for (int i = threadIdx.x - 64; i < 2 * BN; i += 128) p.stats[(size_t)blockIdx.x * 2 * BN + i] = s_stats[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static bool pick_tile(int mode, int H, int W, int* TW, int* TH) {
+  // tile = TH x TW = 128 pixels, TW a multiple of 8 (one SWIZZLE_128B atom = 8 pixel rows)
+  if (mode == MODE_CONV3) {
+    *TW = (W > 8 && H <= 8) ? 16 : 8;
+    *TH = 128 / *TW;
+    return true;
+  }
+  // no halo: prefer the widest tile that does not waste columns
+  const int cand[5] = {8, 16, 32, 64, 128};
+  int best = 8;
+  long best_cost = -1;
+  for (int i = 0; i < 5; ++i) {
+    const int tw = cand[i], th = 128 / tw;
+    const long cost = (long)ceil_div(W, tw) * tw * ceil_div(H, th) * th;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = tw;
+    }
+  }
+  *TW = best;
+  *TH = 128 / best;
+  return true;
+}
+
+static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int box_w, int box_h) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  uint32_t box[4] = {64, (uint32_t)box_w, (uint32_t)box_h, 1};
+  return encode_tmap_bf16(m, base, 4, dims, str, box);
+}
+// view of a (N, 2H, 2W, C) tensor as (sc = s*C + c, w, r, h, n): pixel (2h+r, 2w+s)
+static int make_up_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int box_w, int box_h) {
+  uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)W, 2, (uint64_t)H, (uint64_t)N};
+  uint64_t str[4] = {(uint64_t)2 * C * 2, (uint64_t)2 * W * C * 2, (uint64_t)4 * W * C * 2, (uint64_t)4 * H * W * C * 2};
+  uint32_t box[5] = {64, (uint32_t)box_w, 1, (uint32_t)box_h, 1};
+  return encode_tmap_bf16(m, base, 5, dims, str, box);
+}
+static int make_w_map(CUtensorMap* m, const void* base, int taps, int n_rows, int k, int box_n, int box_taps) {
+  uint64_t dims[3] = {(uint64_t)k, (uint64_t)n_rows, (uint64_t)taps};
+  uint64_t str[2] = {(uint64_t)k * 2, (uint64_t)n_rows * k * 2};
+  uint32_t box[3] = {64, (uint32_t)box_n, (uint32_t)box_taps};
+  return encode_tmap_bf16(m, base, 3, dims, str, box);
+}
+
+template <int BN>
+static int launch_k1(const K1Params& p, int grid, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CMU_CHECK_CUDA(cudaFuncSetAttribute(k1_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Cfg<BN>::kSmem));
+    attr_set = true;
+  }
+  k1_kernel<BN><<<grid, kK1Threads, K1Cfg<BN>::kSmem, stream>>>(p);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+// Generic driver used by the C-ABI entry points below.
+int simt_k1(int mode, const void* a0, int c0, const void* a1, int c1, int N, int H, int W, const void* wpk, int n_total,
+            void* out0, int oc0, void* out1, int oc1, const float* bias, int bias_mod, float* stats_partial,
+            int* stats_grid, cudaStream_t st);
+
+static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int N, int H, int W, const void* wpk,
+                  int n_total, void* out0, int oc0, void* out1, int oc1, const float* bias, int bias_mod,
+                  float* stats_partial, int* stats_grid, int* stats_bn, cudaStream_t stream) {
+  if (debug_knob(0) == 1) {  // CUDA-core cross-check path (tests / debugging only)
+    if (stats_bn) *stats_bn = n_total;
+    return simt_k1(mode, a0, c0, a1, c1, N, H, W, wpk, n_total, out0, oc0, out1, oc1, bias, bias_mod, stats_partial,
+                   stats_grid, stream);
+  }
+  CMU_REQUIRE(c0 > 0 && c0 % 64 == 0 && c1 % 64 == 0, "k1: channel counts must be multiples of 64 (c0=%d c1=%d)", c0, c1);
+  CMU_REQUIRE(n_total % 64 == 0, "k1: GEMM-N must be a multiple of 64 (got %d)", n_total);
+  K1Params p;
+  memset(&p, 0, sizeof(p));
+  p.mode = mode;
+  p.N = N; p.H = H; p.W = W;
+  p.c0 = c0; p.c1 = c1;
+  p.n_total = n_total;
+  p.oc0 = oc0;
+  pick_tile(mode, H, W, &p.TW, &p.TH);
+  p.tw_shift = __builtin_ctz(p.TW);
+  p.tiles_w = ceil_div(W, p.TW);
+  p.tiles_h = ceil_div(H, p.TH);
+  p.m_tiles = N * p.tiles_w * p.tiles_h;
+  int BN = (n_total % 128 == 0) ? 128 : 64;
+  CMU_REQUIRE(oc0 % 64 == 0 && oc1 % 64 == 0, "k1: output channel counts must be multiples of 64");
+  if (debug_knob(1) == 64) BN = 64;
+  p.n_tiles = n_total / BN;
+  if (stats_bn) *stats_bn = BN;
+  p.kc = (mode == MODE_CONVT_DGRAD) ? 4 * (c0 / 64) : (c0 + c1) / 64;
+  p.bias = bias;
+  p.bias_mod = bias_mod > 0 ? bias_mod : n_total;
+  p.stats = stats_partial;
+
+  const int box_h = (mode == MODE_CONV3) ? p.TH + 2 : p.TH;
+  if (mode == MODE_CONVT_DGRAD) {
+    if (make_up_map(&p.tmA0, a0, N, H, W, c0, p.TW, p.TH)) return 1;
+    p.tmA1 = p.tmA0;
+  } else {
+    if (make_act_map(&p.tmA0, a0, N, H, W, c0, p.TW, box_h)) return 1;
+    if (a1 != nullptr) {
+      if (make_act_map(&p.tmA1, a1, N, H, W, c1, p.TW, box_h)) return 1;
+    } else {
+      p.tmA1 = p.tmA0;
+    }
+  }
+  const int ktot = p.kc * 64;
+  if (mode == MODE_CONV3) {
+    if (make_w_map(&p.tmB, wpk, 9, n_total, ktot, BN, 3)) return 1;
+  } else {
+    if (make_w_map(&p.tmB, wpk, 1, n_total, ktot, BN, 1)) return 1;
+  }
+  if (mode == MODE_CONVT_FPROP) {
+    if (make_up_map(&p.tmO0, out0, N, H, W, oc0, p.TW, p.TH)) return 1;
+    p.tmO1 = p.tmO0;
+  } else {
+    if (make_act_map(&p.tmO0, out0, N, H, W, oc0, p.TW, p.TH)) return 1;
+    if (out1 != nullptr) {
+      if (make_act_map(&p.tmO1, out1, N, H, W, oc1, p.TW, p.TH)) return 1;
+    } else {
+      p.tmO1 = p.tmO0;
+    }
+  }
+  int grid = num_sms();
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  if (grid > total_tiles) grid = total_tiles;
+  grid = (grid / p.n_tiles) * p.n_tiles;
+  if (grid < p.n_tiles) grid = p.n_tiles;
+  if (stats_grid) *stats_grid = grid;
+  return BN == 128 ? launch_k1<128>(p, grid, stream) : launch_k1<64>(p, grid, stream);
+}
+
+}  // namespace cmu
+
+using namespace cmu;
+
+extern "C" {
+
+// Upper bound on the number of CTAs (= rows of the statistics partial buffer) any K1 launch uses.
+int cmu_conv_max_grid(void) { return num_sms(); }
+
+int cmu_conv3x3_fprop(const void* x0, int c0, const void* x1, int c1, int n, int h, int w, const void* w_packed,
+                      int cout, void* y, float* stats_partial, int* stats_grid, int* stats_bn, void* stream) {
+  return run_k1(MODE_CONV3, x0, c0, x1, c1, n, h, w, w_packed, cout, y, cout, nullptr, 0, nullptr, 0, stats_partial,
+                stats_grid, stats_bn, (cudaStream_t)stream);
+}
+
+int cmu_conv3x3_dgrad(const void* dy, int cout, int n, int h, int w, const void* w_packed_dgrad, void* dx0, int c0,
+                      void* dx1, int c1, void* stream) {
+  return run_k1(MODE_CONV3, dy, cout, nullptr, 0, n, h, w, w_packed_dgrad, c0 + c1, dx0, c0, dx1, c1, nullptr, 0,
+                nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int cmu_conv1x1_fprop(const void* x, int cin, int n, int h, int w, const void* w_packed, int cout, const float* bias,
+                      void* y, void* stream) {
+  return run_k1(MODE_PLAIN, x, cin, nullptr, 0, n, h, w, w_packed, cout, y, cout, nullptr, 0, bias, cout, nullptr,
+                nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int cmu_convT2x2_fprop(const void* x, int cin, int n, int h, int w, const void* w_packed, int cout, const float* bias,
+                       void* y, void* stream) {
+  return run_k1(MODE_CONVT_FPROP, x, cin, nullptr, 0, n, h, w, w_packed, 4 * cout, y, cout, nullptr, 0, bias, cout,
+                nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int cmu_convT2x2_dgrad(const void* dy, int cout, int n, int h, int w, const void* w_packed_dgrad, int cin, void* dx,
+                       void* stream) {
+  return run_k1(MODE_CONVT_DGRAD, dy, cout, nullptr, 0, n, h, w, w_packed_dgrad, cin, dx, cin, nullptr, 0, nullptr, 0,
+                nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+/* cmu_b200.h — C ABI of libcmu_b200.so: the B200 (sm_100a) kernels behind the CM-UNet pretraining / fine-tuning
+ * hot path.  Plain pointers and sizes only; no torch types.  This is exactly the surface a binding of the
+ * reference's modules would call (see INTEGRATION.md for the ctypes stub).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; the message is in cmu_last_error() (thread local).
+ *   - all pointers are DEVICE pointers unless the name starts with h_; `stream` is a cudaStream_t passed as void*.
+ *   - activations: NHWC bf16 ("act"), channel counts multiples of 64 (except the 1-channel input image and the
+ *     2-channel head output, which stay fp32 in the reference's NCHW layout).
+ *   - the caller owns every buffer including workspaces; the library never allocates device memory, keeps no
+ *     pointers after a call returns and performs no host synchronisation.
+ *   - unsupported shapes / architectures are errors (there is no CPU or library fallback).
+ *
+ * Each entry point cites the reference code it replaces (paths relative to the reference repository root;
+ * CMU = Pretraining/CM-UNet/cmae/models, FT = Finetuning).
+ */
+#ifndef CMU_B200_H
+#define CMU_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- runtime ------------------------------------------------------------------------------------------- */
+const char* cmu_last_error(void);
+int cmu_version(void);
+int cmu_device_check(void);               /* current device must be sm_100 */
+int cmu_debug_set(int key, int value);    /* 0: 1 = CUDA-core cross-check path for the conv GEMMs (tests only)
+                                             1: 64 = force 64-wide N tiles; 2: descriptor experiment switch */
+
+/* ---- a1  patch-mask generator: CMU/backbones/UNet_encoder.py:106-139 (create_random_patch_mask) ------------
+ * d_state: uint32[cmu_mask_state_words()] = MT19937 key[624] + position, same content as numpy's
+ * np.random.get_state()[1:3] (legacy global RNG used at UNet_encoder.py:124).  Bit-exact with the reference. */
+int cmu_mask_state_words(void);
+int cmu_mask_seed(unsigned int* d_state, unsigned int seed, void* stream);             /* == np.random.seed(seed) */
+int cmu_mask_generate(unsigned int* d_state, unsigned char* mask /* (batch,S,S) u8 or NULL */, int* perm_ws /* int32[batch*K] */,
+                      int batch, int img_size, int patch_size, int k_masked, int n_shuffles, void* stream);
+
+/* ---- a2/a3  DoubleConv pieces: CMU/backbones/UNet_encoder.py:18-30,141-158 == FT/model.py:16-26 ----------- */
+/* weight packing (fp32 torch layouts -> bf16 GEMM operands); wf / wd may be NULL */
+int cmu_pack_conv3x3_weights(const float* w /* (Cout,Cin,3,3) */, int cout, int cin, void* wf /* [9][Cout][Cin] */,
+                             void* wd /* [9][Cin][Cout], rotated */, void* stream);
+int cmu_pack_convT2x2_weights(const float* w /* (Cin,Cout,2,2) */, int cin, int cout, void* wf /* [4*Cout][Cin] */,
+                              void* wd /* [Cin][4*Cout] */, void* stream);
+int cmu_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream);
+
+/* first conv, Cin = 1, fused with x * (1 - mask[0]) (UNet_encoder.py:156, quirk Q1); stats_partial:
+ * float[cmu_conv3x3_c1_grid()][2][64] per-block (sum, sumsq) of the fp32 outputs, or NULL */
+int cmu_conv3x3_c1_grid(void);
+int cmu_conv3x3_c1_fprop(const float* x /* (N,H,W) */, const unsigned char* mask0 /* (H,W) or NULL */,
+                         const float* w /* (64,1,3,3) */, int cout, void* y /* act (N,H,W,64) */, float* stats_partial,
+                         int n, int h, int w_, void* stream);
+int cmu_conv3x3_c1_wgrad(const float* x, const unsigned char* mask0, const void* dy, int cout,
+                         float* partial /* float[grid][576] */, float* dw /* (64,1,3,3) */, int accumulate, int n, int h,
+                         int w_, void* stream);
+
+/* conv3x3 pad 1 as tcgen05 implicit GEMM.  (x0|x1) = channel concat of two act tensors (munet_neck.py:48; x1 may be
+ * NULL).  The conv bias is NOT applied (it cancels inside the train-mode BN that always follows; cmu_bn_finalize
+ * folds it into running_mean / the eval shift).  stats_partial: float[*stats_grid][2][*stats_bn] per-CTA
+ * (sum, sumsq) of the fp32 accumulators; size it with cmu_conv_max_grid() * 2 * 128. */
+int cmu_conv_max_grid(void);
+int cmu_conv3x3_fprop(const void* x0, int c0, const void* x1, int c1, int n, int h, int w, const void* w_packed, int cout,
+                      void* y, float* stats_partial, int* h_stats_grid, int* h_stats_bn, void* stream);
+int cmu_conv3x3_dgrad(const void* dy, int cout, int n, int h, int w, const void* w_packed_dgrad, void* dx0, int c0,
+                      void* dx1, int c1, void* stream);
+long long cmu_conv3x3_wgrad_workspace_bytes(int cin, int cout, int n, int h, int w);
+int cmu_conv3x3_wgrad(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout, int n, int h, int w,
+                      float* workspace, long long workspace_bytes, float* dw /* (Cout,Cin,3,3) fp32 */, int accumulate,
+                      void* stream);
+
+/* BatchNorm2d (train: batch statistics, running stats momentum update with unbiased variance; eval: running stats)
+ * -> per-channel scale/shift; then apply + ReLU (+ MaxPool2d(2), UNet_encoder.py:44-49) */
+int cmu_bn_finalize(const float* partial, int grid, int bn_tile, int c, double count, const float* gamma, const float* beta,
+                    const float* conv_bias, float* running_mean, float* running_var, float momentum, float eps,
+                    int training, float* scale, float* shift, float* mean, float* rstd, void* stream);
+int cmu_bn_relu_apply(const void* y, const float* scale, const float* shift, void* a, void* pooled /* or NULL */, int n,
+                      int h, int w, int c, void* stream);
+/* backward of ReLU + BN (+ pool routing): dy from da (+ dpool); sums = float[2][C] = (dbeta, dgamma) */
+int cmu_bn_bwd_grid(void);
+int cmu_bn_relu_bwd(const void* da, const void* dpool, const void* y, const float* scale, const float* shift,
+                    const float* mean, const float* rstd, float* partial /* float[grid][2][C] */, float* sums, void* dy,
+                    int n, int h, int w, int c, void* stream);
+
+/* ---- a5  UpBlock pieces: CMU/necks/munet_neck.py:25-49 == FT/model.py:57-81 ------------------------------ */
+int cmu_convT2x2_fprop(const void* x, int cin, int n, int h, int w, const void* w_packed, int cout, const float* bias,
+                       void* y /* act (N,2H,2W,Cout) */, void* stream);
+int cmu_convT2x2_dgrad(const void* dy, int cout, int n, int h, int w, const void* w_packed_dgrad, int cin, void* dx,
+                       void* stream);
+long long cmu_convT2x2_wgrad_workspace_bytes(int cin, int cout, int n, int h, int w);
+int cmu_convT2x2_wgrad(const void* x, int cin, const void* dy, int cout, int n, int h, int w, float* workspace,
+                       long long workspace_bytes, float* dw /* (Cin,Cout,2,2) */, int accumulate, void* stream);
+int cmu_colsum_bf16(const void* x /* (rows, C) bf16 */, long long rows, int c, float* partial /* float[grid][C] */,
+                    float* out /* float[C] */, void* stream);   /* ConvTranspose2d bias gradient */
+
+/* ---- a6  1x1 heads: munet_neck.py:72 (conv_last 64->2), cmunet.py:128-129 (reduce_channels 1024->256) ---- */
+int cmu_conv1x1_fprop(const void* x, int cin, int n, int h, int w, const void* w_packed /* bf16 [Cout][Cin] */, int cout,
+                      const float* bias, void* y, void* stream);
+int cmu_head1x1_fprop(const void* a, const float* w, const float* b, float* out /* (N,2,H,W) fp32 */, int n, int h, int w_,
+                      int cin, int cout, void* stream);
+int cmu_head1x1_bwd(const void* a, const float* w, const float* dout, void* da, float* acc /* float[130] */, int n, int h,
+                    int w_, int cin, int cout, void* stream);
+
+/* ---- a7  NonLinearNeck: CMU/necks/nonlinear_neck.py:88-103 ------------------------------------------------ */
+long long cmu_sgemm_workspace_bytes(int m, int n, int k);
+int cmu_sgemm(const float* a, long long sam, long long sak, const float* b, long long sbn, long long sbk, float* c,
+              long long ldc, const float* bias, int m, int n, int k, int accumulate, float* workspace,
+              long long workspace_bytes, void* stream);
+int cmu_colsum(const float* x, int m, int n, float* out, int accumulate, void* stream);
+int cmu_bn1d_stats(const float* x, int m, int c, float* stats /* [2][C] */, void* stream);
+int cmu_bn1d_apply(const float* x, const float* stats, double count, int m, int c, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, float momentum, float eps, int training, int relu, float* y,
+                   float* mean, float* rstd, void* stream);
+int cmu_bn1d_bwd_stats(const float* dy, const float* y, const float* x, const float* mean, const float* rstd, int m, int c,
+                       int relu, float* sums, void* stream);
+int cmu_bn1d_bwd_apply(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
+                       const float* gamma, const float* sums, double count, int m, int c, int relu, float* dx, void* stream);
+int cmu_channel_mean2_bf16(const float* x /* (N,2,HW) */, void* y /* (N,HW) bf16 */, int n, long long hw, void* stream);
+int cmu_channel_mean2_bwd(const float* dx, float* dout, int n, long long hw, void* stream);   /* cmunet.py:126 */
+int cmu_nhwc_to_nchw_bf16(const void* x, void* y, int n, int hw, int c, void* stream);        /* cmunet.py:130 */
+
+/* ---- a9/a10  CMUNetPretrainHead: CMU/heads/cmunet_head.py:62-91 ------------------------------------------- */
+int cmu_masked_mse_fwd(const float* x, const float* pred, long long pred_bstride, const unsigned char* mask, double* acc,
+                       float rc_weight, float* loss, int b, int h, int w, void* stream);
+int cmu_masked_mse_bwd(const float* x, const float* pred, long long pred_bstride, const unsigned char* mask,
+                       const double* acc, const float* gscale, float* dpred, long long dpred_bstride, int b, int h, int w,
+                       void* stream);
+int cmu_l2_normalize_rows(const float* x, float* y, int rows, int dim, void* stream);
+int cmu_infonce_fwd_bwd(const float* q, const float* z, int batch, int n_keys, int dim, int label_offset, float tau,
+                        float ct_weight, float* loss_rows, float* loss, float* dq, void* stream);
+
+/* ---- a12/a16  EMA (cmunet.py:78-92) and AdamW (configs/cmunet_config.py:76-91) ---------------------------- */
+int cmu_ema_chunks(const long long* d_table /* [n][3] = dst, src, count */, int n_chunks, float momentum, void* stream);
+int cmu_adamw_chunks(const long long* d_table /* [n][6] = p, g, m, v, count, decay */, int n_chunks, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+/* ---- a15  fine-tuning losses: FT/metrics.py:135-220,503-504 ----------------------------------------------- */
+int cmu_seg_losses(const float* logits, const double* gt, double* acc /* double[4] */, double* out /* dice, iou, ce */,
+                   float* dlogits /* or NULL */, const float* gscale, int n, int h, int w, double dice_eps, double beta,
+                   double iou_eps, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMU_B200_H */
