@@ -348,12 +348,12 @@ __global__ void seg_losses_finish_kernel(const double* acc, double npix, double 
 }
 
 // ------------------------------------------------------------------------------------------ small layout helpers
-// mean over the 2 channels of (N,2,H,W) fp32 -> (N, H*W) bf16  (cmunet.py:126 feeding projector.fc0)
-__global__ void chmean2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, size_t n_img, size_t hw) {
+// mean over the 2 channels of (N,2,H,W) fp32 -> (N, H*W) fp32  (cmunet.py:126 feeding projector.fc0)
+__global__ void chmean2_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n_img, size_t hw) {
   const size_t total = n_img * hw;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t n = i / hw, p = i % hw;
-    y[i] = __float2bfloat16_rn(0.5f * (x[(n * 2) * hw + p] + x[(n * 2 + 1) * hw + p]));
+    y[i] = 0.5f * (x[(n * 2) * hw + p] + x[(n * 2 + 1) * hw + p]);
   }
 }
 // d(N,2,H,W)[:,c] = 0.5 * dx(N,H*W)  (fp32 in, fp32 out), optionally accumulating
@@ -366,8 +366,11 @@ __global__ void chmean2_bwd_kernel(const float* __restrict__ dx, float* __restri
     dout[(n * 2 + 1) * hw + p] = g;
   }
 }
-// (N, HW, C) bf16 -> (N, C, HW) bf16 through a 32x32 smem tile  (cmunet.py:130 flattens NCHW order)
-__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int hw, int c) {
+// (N, HW, C) bf16 -> (N, C, HW) bf16 / fp32 through a 32x32 smem tile  (cmunet.py:130 flattens NCHW order)
+__device__ __forceinline__ void store_out(__nv_bfloat16* p, __nv_bfloat16 v) { *p = v; }
+__device__ __forceinline__ void store_out(float* p, __nv_bfloat16 v) { *p = __bfloat162float(v); }
+template <typename OutT>
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, OutT* __restrict__ y, int hw, int c) {
   __shared__ __nv_bfloat16 tile[32][33];
   const size_t n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -378,7 +381,7 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int cc = c0 + r, p = p0 + threadIdx.x;
-    if (p < hw && cc < c) y[(n * c + cc) * hw + p] = tile[threadIdx.x][r];
+    if (p < hw && cc < c) store_out(&y[(n * c + cc) * hw + p], tile[threadIdx.x][r]);
   }
 }
 
@@ -480,9 +483,8 @@ int cmu_seg_losses(const float* logits, const double* gt, double* acc, double* o
   return 0;
 }
 
-int cmu_channel_mean2_bf16(const float* x, void* y, int n, long long hw, void* stream) {
-  chmean2_kernel<<<grid_for((size_t)n * hw, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)y, (size_t)n,
-                                                                                    (size_t)hw);
+int cmu_channel_mean2(const float* x, float* y, int n, long long hw, void* stream) {
+  chmean2_kernel<<<grid_for((size_t)n * hw, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, (size_t)n, (size_t)hw);
   CMU_LAUNCH_CHECK();
   return 0;
 }
@@ -493,7 +495,13 @@ int cmu_channel_mean2_bwd(const float* dx, float* dout, int n, long long hw, voi
 }
 int cmu_nhwc_to_nchw_bf16(const void* x, void* y, int n, int hw, int c, void* stream) {
   dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), block(32, 8);
-  nhwc_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, c);
+  nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, hw, c);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+int cmu_nhwc_to_nchw_f32(const void* x, float* y, int n, int hw, int c, void* stream) {
+  dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), block(32, 8);
+  nhwc_to_nchw_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, y, hw, c);
   CMU_LAUNCH_CHECK();
   return 0;
 }

@@ -33,7 +33,6 @@ struct K2Params {
   int m_atoms;         // 1 (M = 64 duplicated to 128) or 2
   int n_cols;          // 64 or 128
   int taps;            // accumulators per CTA: 3 (conv) or 1 (convT)
-  int lbo_sbo_swap;    // debug knob
   float* ws;           // [splits][G*taps][QC][PC]
 };
 
@@ -129,14 +128,9 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
         for (int r = 0; r < p.taps; ++r) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {  // 128 pixels = 8 x K16; 16 pixel rows = 2048 bytes
-            uint64_t ad, bd;
-            if (p.lbo_sbo_swap) {
-              ad = umma_smem_desc(sQ + r * tap_stride + k * 2048, 1024, a_lbo);
-              bd = umma_smem_desc(sP + k * 2048, 1024, b_lbo);
-            } else {
-              ad = umma_smem_desc(sQ + r * tap_stride + k * 2048, a_lbo, 1024);
-              bd = umma_smem_desc(sP + k * 2048, b_lbo, 1024);
-            }
+            // MN-major SWIZZLE_128B: LBO = byte stride between 64-channel atoms, SBO = stride between 8-pixel K groups
+            const uint64_t ad = umma_smem_desc(sQ + r * tap_stride + k * 2048, a_lbo, 1024);
+            const uint64_t bd = umma_smem_desc(sP + k * 2048, b_lbo, 1024);
             umma_bf16(tmem_base + r * p.n_cols, ad, bd, idesc, (it | (uint32_t)k) != 0 ? 1u : 0u);
           }
         }
@@ -281,7 +275,6 @@ static int run_k2(int mode, const void* q0, int qc0, const void* q1, int qc1, co
   p.TW = pl.TW; p.TH = pl.TH; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.pix_tiles = pl.pix_tiles;
   p.MT = pl.MT; p.NT = pl.NT; p.G = pl.G; p.splits = pl.splits;
   p.m_atoms = pl.m_atoms; p.n_cols = pl.n_cols; p.taps = pl.taps;
-  p.lbo_sbo_swap = debug_knob(2);
   p.ws = ws;
   if (make_act_map4(&p.tmP, pten, N, H, W, pc, pl.TW, pl.TH)) return 1;
   if (mode == 0) {

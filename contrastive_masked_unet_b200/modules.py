@@ -1,0 +1,493 @@
+"""Drop-in `torch.nn.Module`s for the CM-UNet pretraining path: same class names, constructor kwargs, forward
+signatures, return structures and state_dict keys as the reference
+(Pretraining/CM-UNet/cmae/models/{backbones/UNet_encoder.py, necks/munet_neck.py, necks/nonlinear_neck.py,
+heads/cmunet_head.py, algorithms/cmunet.py, algorithms/base.py}); the math runs in libcmu_b200.so.
+
+The `nn.Conv2d` / `nn.BatchNorm2d` / `nn.Linear` children exist only as PARAMETER CONTAINERS (they give the
+reference's key names, default initialisation and RNG consumption); their own forward is never called.
+CUDA (sm_100a) only: CPU tensors raise, there is no fallback."""
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import functional as Fn
+from . import ops
+from ._lib import CmuError, lib
+
+MODELS = {}
+
+
+def register(cls):
+    MODELS[cls.__name__] = cls
+    return cls
+
+
+def build(cfg):
+    """Minimal stand-in for mmengine's `MODELS.build(cfg)` (cmae/registry.py:83-84)."""
+    if isinstance(cfg, nn.Module):
+        return cfg
+    cfg = dict(cfg)
+    typ = cfg.pop('type')
+    cls = MODELS[typ] if isinstance(typ, str) else typ
+    return cls(**cfg)
+
+
+# --------------------------------------------------------------------------------------------------------- mask stream
+class MaskStream:
+    """Device-resident MT19937 stream that continues numpy's legacy global RNG bit-for-bit
+    (UNet_encoder.py:124 `np.random.shuffle`).  By default it is seeded lazily from `np.random.get_state()` at first
+    use, so `np.random.seed(s)` before training gives the reference's masks (quirk Q2: online and target encoders
+    share ONE stream, online first)."""
+
+    def __init__(self):
+        self.state = None
+
+    def _ensure(self, device):
+        if self.state is None:
+            self.set_numpy_state(np.random.get_state(), device)
+        elif self.state.device != device:
+            self.state = self.state.to(device)
+
+    def seed(self, seed, device='cuda'):
+        self.state = torch.empty(lib.cmu_mask_state_words(), dtype=torch.int32, device=device)
+        lib.cmu_mask_seed(self.state.data_ptr(), int(seed) & 0xFFFFFFFF, ops._stream())
+
+    def set_numpy_state(self, np_state, device='cuda'):
+        assert np_state[0] == 'MT19937'
+        words = np.concatenate([np.asarray(np_state[1], dtype=np.uint32), np.array([np_state[2]], dtype=np.uint32)])
+        self.state = torch.from_numpy(words.view(np.int32).copy()).to(device)
+
+    def get_numpy_state(self):
+        w = self.state.cpu().numpy().view(np.uint32)
+        return ('MT19937', w[:624].copy(), int(w[624]), 0, 0.0)
+
+    def generate(self, batch, img_size, patch_size, mask_ratio, device):
+        """One `create_random_patch_mask` call: consumes `batch` shuffles, returns the (B,S,S) uint8 mask."""
+        self._ensure(device)
+        g = img_size // patch_size
+        k = min(int(mask_ratio * img_size * img_size) // (patch_size * patch_size), g * g)
+        mask = torch.empty(batch, img_size, img_size, dtype=torch.uint8, device=device)
+        ws = torch.empty(max(batch * k, 1), dtype=torch.int32, device=device)
+        lib.cmu_mask_generate(self.state.data_ptr(), mask.data_ptr(), ws.data_ptr(), batch, img_size, patch_size, k, batch,
+                              ops._stream())
+        return mask, k
+
+
+# --------------------------------------------------------------------------------------------------------- conv blocks
+def _bn_cfg(bn, pool):
+    mom = bn.momentum if bn.momentum is not None else 0.1
+    return Fn.BNConfig(bn.training, mom, bn.eps, pool)
+
+
+def _conv_bn_relu(conv, bn, x0, x1=None, pool=False):
+    if bn.training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return Fn.ConvBNReLUFn.apply(Fn.to_act(x0), None if x1 is None else Fn.to_act(x1), conv.weight, conv.bias, bn.weight,
+                                 bn.bias, bn.running_mean, bn.running_var, _bn_cfg(bn, pool))
+
+
+@register
+class DoubleConv(nn.Module):
+    """[Conv3x3 -> BatchNorm2d -> ReLU] x 2 (UNet_encoder.py:8-30)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.double_conv = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1), nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1), nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True))
+        self.in_channels, self.out_channels = in_channels, out_channels
+
+    def run(self, x, skip=None, mask=None, pool=False):
+        """x: NCHW-shaped tensor (fp32 (N,1,H,W) for the first layer); skip: second concat source; mask: (B,H,W) uint8
+        whose image 0 masks the whole batch (first layer only)."""
+        seq = self.double_conv
+        ops._need_cuda(x)
+        if self.in_channels == 1:
+            bn = seq[1]
+            if bn.training and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+            a = Fn.FirstConvBNReLUFn.apply(x.reshape(x.shape[0], x.shape[-2], x.shape[-1]), mask, seq[0].weight,
+                                           seq[0].bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                           _bn_cfg(bn, False))
+        else:
+            if mask is not None:
+                raise CmuError('input masking is fused into the 1-channel first layer only')
+            a = _conv_bn_relu(seq[0], seq[1], x, skip, False)
+        return _conv_bn_relu(seq[3], seq[4], a, None, pool)
+
+    def forward(self, x):
+        return self.run(x)
+
+
+@register
+class DownBlock(nn.Module):
+    """DoubleConv then MaxPool2d(2); returns (down, skip) (UNet_encoder.py:32-49)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.double_conv = DoubleConv(in_channels, out_channels)
+        self.down_sample = nn.MaxPool2d(2)
+
+    def forward(self, x, mask=None):
+        skip_out, down_out = self.double_conv.run(x, mask=mask, pool=True)
+        return (down_out, skip_out)
+
+
+@register
+class UpBlock(nn.Module):
+    """ConvTranspose2d(k2,s2) -> cat([up, skip]) -> DoubleConv (munet_neck.py:11-49).  The concat is never
+    materialised: the following conv reads its K range from the two tensors."""
+
+    def __init__(self, in_channels, out_channels, up_sample_mode):
+        super().__init__()
+        if up_sample_mode == 'conv_transpose':
+            self.up_sample = nn.ConvTranspose2d(in_channels, out_channels, kernel_size=2, stride=2)
+        elif up_sample_mode == 'bilinear':
+            self.up_sample = nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)
+        else:
+            raise ValueError("Unsupported `up_sample_mode` (can take one of `conv_transpose` or `bilinear`)")
+        self.up_sample_mode = up_sample_mode
+        self.double_conv = DoubleConv(in_channels, out_channels)
+
+    def forward(self, down_input, skip_input):
+        if self.up_sample_mode != 'conv_transpose':
+            raise NotImplementedError('bilinear up-sampling has no sm_100a kernel (and is shape-inconsistent in the '
+                                      'reference: munet_neck.py:29-33)')
+        up = Fn.ConvT2x2Fn.apply(Fn.to_act(down_input), self.up_sample.weight, self.up_sample.bias)
+        return self.double_conv.run(up, skip=skip_input)
+
+
+def _kaiming_init(module):
+    """UNet_encoder.py:86-104 / munet_neck.py:90-110."""
+    for m in module.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.BatchNorm2d):
+            nn.init.constant_(m.weight, 1)
+            nn.init.zeros_(m.bias)
+        elif isinstance(m, nn.Linear):
+            nn.init.xavier_normal_(m.weight)
+            if m.bias is not None:
+                nn.init.zeros_(m.bias)
+
+
+@register
+class UNet_encoder(nn.Module):
+    """UNet_encoder.py:51-158.  forward(x:(B,H,W)) -> (latent, mask uint8 (B,H,W) on x's device, [skip1..4])."""
+
+    def __init__(self, out_classes=2, up_sample_mode='conv_transpose', patch_size=16, mask_ratio=0.65):
+        super().__init__()
+        self.up_sample_mode = up_sample_mode
+        self.down_conv1 = DownBlock(1, 64)
+        self.down_conv2 = DownBlock(64, 128)
+        self.down_conv3 = DownBlock(128, 256)
+        self.down_conv4 = DownBlock(256, 512)
+        self.double_conv = DoubleConv(512, 1024)
+        self.patch_size = patch_size
+        self.mask_ratio = mask_ratio
+        self.mask_stream = MaskStream()
+
+    def forward(self, x):
+        ops._need_cuda(x)
+        b, s = x.shape[0], x.shape[1]
+        mask, k = self.mask_stream.generate(b, s, self.patch_size, self.mask_ratio, x.device)
+        x = x.unsqueeze(1)
+        x, skip1_out = self.down_conv1(x, mask=mask if k > 0 else None)     # fused x * (1 - mask[0])  (:156, Q1)
+        x, skip2_out = self.down_conv2(x)
+        x, skip3_out = self.down_conv3(x)
+        x, skip4_out = self.down_conv4(x)
+        x = self.double_conv(x)
+        return x, mask, [skip1_out, skip2_out, skip3_out, skip4_out]
+
+    def init_weights(self):
+        _kaiming_init(self)
+
+    def create_random_patch_mask(self, batch_size, img_size=256):
+        """UNet_encoder.py:106-139 — returns the mask as a numpy array like the reference (device stream, D2H copy)."""
+        dev = self.mask_stream.state.device if self.mask_stream.state is not None else torch.device('cuda')
+        mask, _ = self.mask_stream.generate(batch_size, img_size, self.patch_size, self.mask_ratio, dev)
+        return mask.cpu().numpy()
+
+    def random_masking(self, x):
+        """UNet_encoder.py:141-158 (API compatibility; forward() uses the fused first-layer path instead)."""
+        mask, _ = self.mask_stream.generate(x.shape[0], x.shape[2], self.patch_size, self.mask_ratio, x.device)
+        return x * (1 - mask[0]), mask.cpu().numpy()
+
+
+@register
+class MUNetPretrainDecoder(nn.Module):
+    """munet_neck.py:51-110.  forward(latent, [skip1..4]) -> (B, out_classes, H, W) fp32."""
+
+    def __init__(self, out_classes=2, up_sample_mode='conv_transpose', init_cfg=None):
+        super().__init__()
+        self.up_sample_mode = up_sample_mode
+        self.up_conv4 = UpBlock(1024, 512, self.up_sample_mode)
+        self.up_conv3 = UpBlock(512, 256, self.up_sample_mode)
+        self.up_conv2 = UpBlock(256, 128, self.up_sample_mode)
+        self.up_conv1 = UpBlock(128, 64, self.up_sample_mode)
+        self.conv_last = nn.Conv2d(64, out_classes, kernel_size=1)
+        self.init_cfg = init_cfg
+
+    def forward(self, x, skip):
+        x = self.up_conv4(x, skip[3])
+        x = self.up_conv3(x, skip[2])
+        x = self.up_conv2(x, skip[1])
+        x = self.up_conv1(x, skip[0])
+        return Fn.Head1x1Fn.apply(Fn.to_act(x), self.conv_last.weight, self.conv_last.bias)
+
+    def init_weights(self):
+        """munet_neck.py:84-88: only recurses (quirk Q6: the decoder keeps PyTorch's default initialisation)."""
+        return None
+
+
+@register
+class NonLinearNeck(nn.Module):
+    """nonlinear_neck.py:7-103: fc0 - bn0 - [relu - fc_i - bn_i].  `norm_cfg` type SyncBN -> statistics are all-reduced
+    over the default process group when world size > 1."""
+
+    def __init__(self, in_channels, hid_channels, out_channels, num_layers=2, with_bias=False, with_last_bn=True,
+                 with_last_bn_affine=True, with_last_bias=False, with_avg_pool=True,
+                 norm_cfg=dict(type='SyncBN', eps=1e-6),
+                 init_cfg=[dict(type='Constant', val=1, layer=['_BatchNorm', 'GroupNorm'])]):
+        super().__init__()
+        self.init_cfg = init_cfg
+        self.with_avg_pool = with_avg_pool
+        if with_avg_pool:
+            self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.relu = nn.ReLU(inplace=True)
+        ncfg = dict(norm_cfg)
+        self.sync = ncfg.pop('type', 'SyncBN') == 'SyncBN'
+        ncfg.pop('requires_grad', None)
+        self.fc0 = nn.Linear(in_channels, hid_channels, bias=with_bias)
+        self.bn0 = nn.BatchNorm1d(hid_channels, **ncfg)
+        self.fc_names, self.bn_names = [], []
+        for i in range(1, num_layers):
+            last = i == num_layers - 1
+            this_channels = out_channels if last else hid_channels
+            self.add_module(f'fc{i}', nn.Linear(hid_channels, this_channels, bias=with_last_bias if last else with_bias))
+            if not last:
+                self.add_module(f'bn{i}', nn.BatchNorm1d(this_channels, **ncfg))
+                self.bn_names.append(f'bn{i}')
+            elif with_last_bn:
+                self.add_module(f'bn{i}', nn.BatchNorm1d(this_channels, **dict(ncfg, affine=with_last_bn_affine)))
+                self.bn_names.append(f'bn{i}')
+            else:
+                self.bn_names.append(None)
+            self.fc_names.append(f'fc{i}')
+
+    def _bn(self, bn, x, relu):
+        if bn.training and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+        mom = bn.momentum if bn.momentum is not None else 0.1
+        return Fn.BN1dFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.training, mom, bn.eps, relu,
+                               self.sync)
+
+    def forward(self, x):
+        ops._need_cuda(x)
+        if self.with_avg_pool:
+            raise NotImplementedError('with_avg_pool=True has no sm_100a kernel (cmunet_config.py uses False)')
+        x = x[:, 0, :]
+        x = x.reshape(x.size(0), -1)
+        x = Fn.LinearFn.apply(x, self.fc0.weight, self.fc0.bias)
+        n_stage = len(self.fc_names)
+        x = self._bn(self.bn0, x, relu=n_stage > 0)                     # the ReLU of the first loop turn is fused here
+        for i, (fc_name, bn_name) in enumerate(zip(self.fc_names, self.bn_names)):
+            fc = getattr(self, fc_name)
+            x = Fn.LinearFn.apply(x, fc.weight, fc.bias)
+            if bn_name is not None:
+                x = self._bn(getattr(self, bn_name), x, relu=i + 1 < n_stage)
+            elif i + 1 < n_stage:
+                raise NotImplementedError('a ReLU that does not follow a BN layer')
+        return x.unsqueeze(dim=1)
+
+    def init_weights(self):
+        for m in self.modules():   # init_cfg: Constant(val=1) on _BatchNorm layers
+            if isinstance(m, nn.modules.batchnorm._BatchNorm) and m.weight is not None:
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+
+def _rank_world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+@torch.no_grad()
+def concat_all_gather(tensor):
+    """cmunet_head.py:9-22."""
+    _, world = _rank_world()
+    if world == 1:
+        return tensor
+    parts = [torch.empty_like(tensor) for _ in range(world)]
+    dist.all_gather(parts, tensor.contiguous())
+    return torch.cat(parts, dim=0)
+
+
+@register
+class CMUNetPretrainHead(nn.Module):
+    """cmunet_head.py:25-91.  forward(x, pred_pixel, mask_s, proj_s, proj_t) -> {'loss_ct', 'loss_rc'}."""
+
+    def __init__(self, predictor, temperature=0.07, ct_weight=1.0, rc_weight=1.0, init_cfg=None):
+        super().__init__()
+        self.predictor = build(predictor)
+        self.t = temperature
+        self.ct_weight = ct_weight
+        self.rc_weight = rc_weight
+        self.criterion = nn.CrossEntropyLoss()
+
+    def forward(self, x, pred_pixel, mask_s, proj_s, proj_t):
+        ops._need_cuda(x, pred_pixel)
+        loss_rc = Fn.MaskedMSEFn.apply(x, pred_pixel, mask_s, self.rc_weight)
+        pred_s = self.predictor(proj_s).squeeze(dim=1)
+        with torch.no_grad():
+            z = ops.l2_normalize_rows(proj_t.squeeze(dim=1).contiguous().float())
+            z_all = concat_all_gather(z)
+        rank, _ = _rank_world()
+        bs = pred_s.size(0)
+        loss_ct = Fn.InfoNCEFn.apply(pred_s, z_all, bs * rank, self.t, self.ct_weight)
+        return {'loss_ct': loss_ct, 'loss_rc': loss_rc}
+
+    def init_weights(self):
+        self.predictor.init_weights()
+
+
+@register
+class CM_UNet(nn.Module):
+    """algorithms/cmunet.py:7-135 (+ algorithms/base.py:75-113 mode dispatch)."""
+
+    def __init__(self, backbone, neck, head, base_momentum=0.996, init_cfg=None, target_cls=True,
+                 persistent_reduce=False, **kwargs):
+        super().__init__()
+        assert neck is not None and head is not None
+        self.init_cfg = init_cfg
+        self.backbone = build(backbone['online'])
+        self.target_backbone = build(backbone['target'])
+        self.pixel_decoder = build(neck['pixel'])
+        self.feature_decoder = build(neck['feature'])
+        self.projector = build(neck['projector'])
+        self.target_projector = build(neck['projector'])
+        self.target_cls = target_cls
+        self.head = build(head)
+        self.base_momentum = base_momentum
+        self.momentum = base_momentum
+        for p in self.target_backbone.parameters():
+            p.requires_grad = False
+        for p in self.target_projector.parameters():
+            p.requires_grad = False
+        # one numpy-compatible mask stream shared by both encoders, online first (quirk Q2)
+        self.target_backbone.mask_stream = self.backbone.mask_stream
+        # Q3: the reference draws a fresh, untrained Conv2d(1024,256,1) in every forward_train (cmunet.py:128).
+        # persistent_reduce=True (opt-in) keeps the first draw.
+        self.persistent_reduce = persistent_reduce
+        self._reduce = None
+        self._ema_table = None
+
+    # ----------------------------------------------------------------------------------- reference API
+    def init_weights(self):
+        """cmunet.py:61-76 after mmengine's BaseModule recursion over children (online encoder first)."""
+        for m in (self.backbone, self.target_backbone, self.pixel_decoder, self.feature_decoder, self.projector,
+                  self.target_projector, self.head):
+            m.init_weights()
+        with torch.no_grad():
+            for pb, pm in zip(self.backbone.parameters(), self.target_backbone.parameters()):
+                pm.copy_(pb)
+                pm.requires_grad = False
+            for pb, pm in zip(self.projector.parameters(), self.target_projector.parameters()):
+                pm.copy_(pb)
+                pm.requires_grad = False
+
+    def _ema_pairs(self):
+        pairs = list(zip(self.backbone.parameters(), self.target_backbone.parameters()))
+        pairs += list(zip(self.projector.parameters(), self.target_projector.parameters()))
+        return pairs
+
+    @torch.no_grad()
+    def momentum_update(self):
+        """cmunet.py:78-92 as ONE multi-tensor launch, in place (theta_t = theta_t*m + theta_o*(1-m))."""
+        pairs = self._ema_pairs()
+        key = tuple((pm.data_ptr(), pb.data_ptr(), pm.numel()) for pb, pm in pairs)
+        if self._ema_table is None or self._ema_table[0] != key:
+            chunk = 1 << 16
+            rows = []
+            for dst, src, n in key:
+                for off in range(0, n, chunk):
+                    rows.append((dst + 4 * off, src + 4 * off, min(chunk, n - off)))
+            dev = pairs[0][1].device
+            self._ema_table = (key, torch.tensor(rows, dtype=torch.int64, device=dev), len(rows))
+        ops._need_cuda(pairs[0][1])
+        lib.cmu_ema_chunks(self._ema_table[1].data_ptr(), self._ema_table[2], float(self.momentum), ops._stream())
+
+    def extract_feat(self, img):
+        return self.backbone(img)
+
+    def _reduce_params(self, device):
+        if self._reduce is None or not self.persistent_reduce:
+            conv = nn.Conv2d(1024, 256, kernel_size=1)             # same CPU torch-RNG consumption as cmunet.py:128
+            w = ops.cast_bf16(conv.weight.detach().to(device).reshape(256, 1024))
+            self._reduce = (w, conv.bias.detach().to(device).float().contiguous())
+        return self._reduce
+
+    def forward_train(self, img, img_t=None, **kwargs):
+        ops._need_cuda(img)
+        latent_s, mask_s, skip_s = self.backbone(img)
+        with torch.no_grad():
+            latent_t, _, _ = self.target_backbone(img_t)
+        pred_pixel = self.pixel_decoder(latent_s, skip_s)
+        pred_feature = self.feature_decoder(latent_s, skip_s)
+        proj_s = self.projector(Fn.ChannelMean2Fn.apply(pred_feature))
+        with torch.no_grad():
+            rw, rb = self._reduce_params(img.device)
+            lt = ops.conv1x1_fprop(Fn._nhwc(Fn.to_act(latent_t)), rw, rb)          # (B,h,w,256) act
+            b, h, w, c = lt.shape
+            flat = torch.empty(b, 1, img.shape[-2], img.shape[-1], dtype=torch.float32, device=img.device)
+            assert c * h * w == img.shape[-2] * img.shape[-1]
+            lib.cmu_nhwc_to_nchw_f32(lt.data_ptr(), flat.data_ptr(), b, h * w, c, ops._stream())   # :130 NCHW flatten
+            proj_t = self.target_projector(flat)                   # mean over the single channel is the identity (:131)
+        return self.head(img, pred_pixel[:, 1], mask_s, proj_s, proj_t)
+
+    def forward(self, img, mode='loss', **kwargs):
+        if mode == 'tensor':
+            return self.extract_feat(img, **kwargs)
+        elif mode == 'loss':
+            return self.forward_train(img, **kwargs)
+        else:
+            raise RuntimeError(f'Invalid mode "{mode}".')
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d['_ema_table'] = None
+        d['_reduce'] = None if not self.persistent_reduce else d['_reduce']
+        return d
+
+
+def cmunet_config(img_size=224, patch_size=16, mask_ratio=0.65):
+    """The model dict of Pretraining/CM-UNet/configs/cmunet_config.py:5-42 with projector.in_channels = S*S."""
+    neck_cfg = dict(type='NonLinearNeck', hid_channels=1536, out_channels=256, num_layers=2, with_bias=True,
+                    with_last_bn=False, with_avg_pool=False)
+    return dict(
+        type='CM_UNet',
+        backbone=dict(online=dict(type='UNet_encoder', patch_size=patch_size, mask_ratio=mask_ratio),
+                      target=dict(type='UNet_encoder', patch_size=patch_size, mask_ratio=0.0)),
+        neck=dict(pixel=dict(type='MUNetPretrainDecoder'), feature=dict(type='MUNetPretrainDecoder'),
+                  projector=dict(neck_cfg, in_channels=img_size * img_size)),
+        head=dict(type='CMUNetPretrainHead', predictor=dict(neck_cfg, in_channels=256), temperature=0.07, ct_weight=1.0,
+                  rc_weight=1.0))
+
+
+def try_register_mmengine():
+    """Registers the drop-in classes under the reference's registry names when mmengine is importable."""
+    try:
+        from mmengine.registry import MODELS as MM
+    except Exception:
+        return False
+    for name, cls in MODELS.items():
+        MM.register_module(name=name, module=cls, force=True)
+    return True

@@ -26,7 +26,7 @@ const char* cmu_last_error(void);
 int cmu_version(void);
 int cmu_device_check(void);               /* current device must be sm_100 */
 int cmu_debug_set(int key, int value);    /* 0: 1 = CUDA-core cross-check path for the conv GEMMs (tests only)
-                                             1: 64 = force 64-wide N tiles; 2: descriptor experiment switch */
+                                             1: 64 = force 64-wide N tiles */
 
 /* ---- a1  patch-mask generator: CMU/backbones/UNet_encoder.py:106-139 (create_random_patch_mask) ------------
  * d_state: uint32[cmu_mask_state_words()] = MT19937 key[624] + position, same content as numpy's
@@ -114,9 +114,10 @@ int cmu_bn1d_bwd_stats(const float* dy, const float* y, const float* x, const fl
                        int relu, float* sums, void* stream);
 int cmu_bn1d_bwd_apply(const float* dy, const float* y, const float* x, const float* mean, const float* rstd,
                        const float* gamma, const float* sums, double count, int m, int c, int relu, float* dx, void* stream);
-int cmu_channel_mean2_bf16(const float* x /* (N,2,HW) */, void* y /* (N,HW) bf16 */, int n, long long hw, void* stream);
+int cmu_channel_mean2(const float* x /* (N,2,HW) */, float* y /* (N,HW) */, int n, long long hw, void* stream);
 int cmu_channel_mean2_bwd(const float* dx, float* dout, int n, long long hw, void* stream);   /* cmunet.py:126 */
 int cmu_nhwc_to_nchw_bf16(const void* x, void* y, int n, int hw, int c, void* stream);        /* cmunet.py:130 */
+int cmu_nhwc_to_nchw_f32(const void* x, float* y, int n, int hw, int c, void* stream);
 
 /* ---- a9/a10  CMUNetPretrainHead: CMU/heads/cmunet_head.py:62-91 ------------------------------------------- */
 int cmu_masked_mse_fwd(const float* x, const float* pred, long long pred_bstride, const unsigned char* mask, double* acc,

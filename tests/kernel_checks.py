@@ -11,6 +11,9 @@ from contrastive_masked_unet_b200._lib import lib
 
 DEV = 'cuda'
 BF16 = torch.bfloat16
+# fp32 references must really be fp32 (cuDNN / cuBLAS would otherwise use TF32)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def nhwc(x):

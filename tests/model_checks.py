@@ -1,0 +1,201 @@
+"""Model-level parity (GPU): the drop-in CUDA modules against the pinned oracle (oracle/cmunet_oracle.py, fp32, same
+device, TF32 off) on identical seeds, weights and synthetic inputs, plus the golden values minted from the reference.
+
+Tolerances (BASELINE.json north_star): masks bit-exact; losses within 1e-2 relative; every parameter gradient whose
+norm is above a noise floor has cosine similarity > 0.999 with the fp32 oracle; conv biases in front of a train-mode BN
+(analytically zero gradient) and pixel_decoder.conv_last channel 0 (quirk Q5) are compared absolutely."""
+import json
+import os
+
+import numpy as np
+import torch
+
+import contrastive_masked_unet_b200 as C
+from oracle import cmunet_oracle as O
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+DEV = 'cuda'
+
+
+def cosine(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-300))
+
+
+def is_zero_grad_key(k):
+    """conv biases feeding train-mode BN: double_conv.{0,3}.bias."""
+    return k.endswith('double_conv.0.bias') or k.endswith('double_conv.3.bias')
+
+
+def build_pair(S, seed):
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    m = C.build(C.cmunet_config(S))
+    m.init_weights()
+    m = m.to(DEV).train()
+    torch.manual_seed(seed)
+    o = O.OracleCMUNet(img_size=S, np_seed=seed)
+    o.init_weights()
+    o = o.to(DEV).train()
+    return m, o
+
+
+def pretrain_parity(S=64, B=8, seed=60, data_seed=1, golden=None, grad_cos=0.999, loss_rtol=1e-2, verbose=False):
+    m, o = build_pair(S, seed)
+    img, img_t = O.synthetic_batch(B, S, data_seed)
+    img, img_t = img.to(DEV), img_t.to(DEV)
+    torch.manual_seed(seed + 1000)
+    lo = o(img, mode='loss', img_t=img_t)
+    (lo['loss_ct'] + lo['loss_rc']).backward()
+    torch.manual_seed(seed + 1000)
+    lm = m(img, mode='loss', img_t=img_t)
+    (lm['loss_ct'] + lm['loss_rc']).backward()
+    torch.cuda.synchronize()
+    rep = {'S': S, 'B': B, 'loss_ct': (float(lm['loss_ct']), float(lo['loss_ct'])),
+           'loss_rc': (float(lm['loss_rc']), float(lo['loss_rc']))}
+    fails = []
+    for name in ('loss_ct', 'loss_rc'):
+        a, b = rep[name]
+        if abs(a - b) > loss_rtol * abs(b):
+            fails.append(f'{name}: {a} vs oracle {b}')
+        if golden is not None and abs(a - golden[name]) > loss_rtol * abs(golden[name]):
+            fails.append(f'{name}: {a} vs golden {golden[name]}')
+    # masks: bit exact (online mask of this step) and RNG stream position
+    from oracle.mask_oracle import MT19937, patch_mask
+    rng = MT19937(seed)
+    ref_mask, _ = patch_mask(rng, B, S, 16, 0.65)
+    # the model returns mask_s only inside forward_train; regenerate through a fresh stream for the bit-exact check
+    ms = C.MaskStream()
+    ms.seed(seed, DEV)
+    got_mask, _ = ms.generate(B, S, 16, 0.65, torch.device(DEV))
+    rep['mask_mismatch'] = int((got_mask.cpu().numpy() != ref_mask).sum())
+    if rep['mask_mismatch']:
+        fails.append('mask mismatch')
+    po = dict(o.named_parameters())
+    worst = (2.0, None)
+    cos_table = {}
+    for k, p in m.named_parameters():
+        g, go = p.grad, po[k].grad
+        if (g is None) != (go is None):
+            fails.append(f'{k}: grad presence differs')
+            continue
+        if g is None:
+            continue
+        gn = float(go.norm())
+        if is_zero_grad_key(k):
+            if float(g.abs().max()) > 1e-4 + 1e-3 * gn:
+                fails.append(f'{k}: expected ~0 gradient, got max {float(g.abs().max())}')
+            continue
+        if k == 'pixel_decoder.conv_last.weight':
+            if float(g[0].abs().max()) != 0.0 and float(g[0].abs().max()) > 1e-6:
+                fails.append('pixel_decoder.conv_last.weight[0] must have zero gradient (Q5)')
+            c = cosine(g[1], go[1])
+        elif k == 'pixel_decoder.conv_last.bias':
+            c = 1.0 if abs(float(g[1] - go[1])) <= 2e-2 * abs(float(go[1])) + 1e-6 else 0.0
+        elif gn < 1e-7:
+            continue
+        else:
+            c = cosine(g, go)
+        cos_table[k] = c
+        if c < worst[0]:
+            worst = (c, k)
+        if c < grad_cos:
+            fails.append(f'{k}: grad cosine {c:.6f} (|g| oracle {gn:.3e})')
+    rep['worst_grad_cos'] = worst
+    rep['n_grads'] = len(cos_table)
+    # BN running statistics after the step
+    bo = dict(o.named_buffers())
+    worst_buf = 0.0
+    for k, b in m.named_buffers():
+        if k.endswith('num_batches_tracked'):
+            if int(b) != int(bo[k]):
+                fails.append(f'{k}: {int(b)} vs {int(bo[k])}')
+            continue
+        err = float((b - bo[k]).abs().max() / bo[k].abs().max().clamp_min(1e-6))
+        worst_buf = max(worst_buf, err)
+        if err > 3e-2:
+            fails.append(f'{k}: running stat rel err {err:.4f}')
+    rep['worst_running_stat_err'] = worst_buf
+    # EMA
+    m.momentum_update()
+    o.momentum_update()
+    torch.cuda.synchronize()
+    ema_err = max(float((a - b).abs().max()) for (_, a), (_, b) in
+                  zip(m.target_backbone.named_parameters(), o.target_backbone.named_parameters()))
+    ema_err = max(ema_err, max(float((a - b).abs().max()) for (_, a), (_, b) in
+                               zip(m.target_projector.named_parameters(), o.target_projector.named_parameters())))
+    rep['ema_max_abs_err'] = ema_err
+    if ema_err > 1e-6:
+        fails.append(f'EMA max abs err {ema_err}')
+    rep['fails'] = fails
+    if verbose:
+        rep['cos_table'] = cos_table
+    return rep
+
+
+def finetune_parity(B=4, S=256, seed=0, golden=None, grad_cos=0.999):
+    torch.manual_seed(seed)
+    net = C.UNet().to(DEV).train()
+    torch.manual_seed(seed)
+    ref = O.OracleUNet().to(DEV).train()
+    x = torch.rand(B, S, S)
+    y1 = (torch.rand(B, 1, S, S) > 0.9)
+    y = torch.cat([~y1, y1], 1).double()
+    x, y = x.to(DEV), y.to(DEV)
+    loss = C.DiceLoss(activation='softmax', threshold=0.5, ignore_channels=[0]) + C.CrossEntropyLoss()
+    iou = C.IoU(activation='softmax', threshold=0.5, ignore_channels=[0])
+    pred = net.forward(x)
+    total = loss(pred, y)
+    total.backward()
+    pr = ref(x)
+    dice_r, ce_r, iou_r = O.dice_loss(pr, y), O.ce_prob_loss(pr, y), O.iou_loss(pr, y)
+    (dice_r + ce_r).backward()
+    torch.cuda.synchronize()
+    dice = float(C.DiceLoss(activation='softmax', threshold=0.5, ignore_channels=[0])(pred, y))
+    ce = float(C.CrossEntropyLoss()(pred, y))
+    rep = {'dice': (dice, float(dice_r)), 'ce': (ce, float(ce_r)), 'iou': (float(iou(pred, y)), float(iou_r)),
+           'total_dtype': str(total.dtype), 'name': loss.__name__,
+           'pred_rel_err': float((pred - pr).abs().max() / pr.abs().max())}
+    fails = []
+    for k in ('dice', 'ce', 'iou'):
+        a, b = rep[k]
+        if abs(a - b) > 1e-2 * abs(b):
+            fails.append(f'{k}: {a} vs {b}')
+        if golden is not None and abs(a - golden[k + '_loss']) > 1e-2 * abs(golden[k + '_loss']):
+            fails.append(f'{k}: {a} vs golden {golden[k + "_loss"]}')
+    if rep['total_dtype'] != 'torch.float64':
+        fails.append('loss must be float64 (Q7)')
+    pr_ref = dict(ref.named_parameters())
+    worst = (2.0, None)
+    for k, p in net.named_parameters():
+        if is_zero_grad_key(k):
+            continue
+        c = cosine(p.grad, pr_ref[k].grad)
+        if c < worst[0]:
+            worst = (c, k)
+        if c < grad_cos:
+            fails.append(f'{k}: grad cosine {c:.6f}')
+    rep['worst_grad_cos'] = worst
+    # eval mode uses running statistics
+    net.eval()
+    ref.eval()
+    with torch.no_grad():
+        pe, pre = net(x), ref(x)
+    rep['eval_rel_err'] = float((pe - pre).abs().max() / pre.abs().max())
+    if rep['eval_rel_err'] > 5e-2:
+        fails.append(f'eval-mode output rel err {rep["eval_rel_err"]}')
+    rep['fails'] = fails
+    return rep
+
+
+def golden_pretrain(S, B):
+    for c in json.load(open(os.path.join(GOLD, 'pretrain.json')))['cases']:
+        if c['S'] == S and c['B'] == B:
+            return c
+    return None
+
+
+def golden_finetune():
+    return json.load(open(os.path.join(GOLD, 'finetune.json')))['case']

@@ -1,0 +1,111 @@
+"""CPU-only checks of the boundary: the C-ABI library builds/loads and exports every symbol include/cmu_b200.h declares
+(no compute calls), the drop-in modules mirror the reference's state_dict / init / error behaviour, and the product path
+fails loudly without CUDA (no CPU fallback)."""
+import io
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import contrastive_masked_unet_b200 as C
+from contrastive_masked_unet_b200._lib import LIB_PATH, parse_header
+from oracle import cmunet_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(LIB_PATH):
+        from contrastive_masked_unet_b200.build import build
+        build()
+    import ctypes
+    dll = ctypes.CDLL(LIB_PATH)
+    protos = parse_header()
+    assert len(protos) >= 45
+    for name in protos:
+        assert hasattr(dll, name), f'{name} declared in include/cmu_b200.h but not exported'
+    out = subprocess.run(['nm', '-D', '--defined-only', LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if ' T ' in l and 'cmu_' in l}
+    assert set(protos) <= exported
+    assert C.lib.cmu_version() >= 100
+    assert C.lib.cmu_mask_state_words() == 625
+
+
+def test_kernels_are_blackwell_native():
+    """SASS of the shipped library contains tcgen05 MMA, TMEM loads and TMA loads/stores (no legacy HMMA)."""
+    out = subprocess.run(['cuobjdump', '-sass', LIB_PATH], capture_output=True, text=True).stdout
+    assert 'UTCHMMA' in out and 'LDTM' in out and 'UTMALDG' in out and 'UTMASTG' in out
+    assert 'HMMA.16816' not in out
+
+
+def test_no_gpu_means_loud_failure():
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(C.CmuError):
+        C.lib.cmu_device_check()
+    m = C.UNet()
+    with pytest.raises(C.CmuError):
+        m(torch.rand(1, 32, 32))
+
+
+def test_state_dict_keys_and_init_match_reference():
+    g = json.load(open(os.path.join(GOLD, 'pretrain.json')))['cases'][0]
+    torch.manual_seed(g['seed'])
+    m = C.build(C.cmunet_config(g['S']))
+    m.init_weights()
+    assert [k for k, _ in m.named_parameters()] == g['param_keys']
+    assert sum(p.numel() for p in m.parameters()) == g['n_params']
+    assert sum(p.numel() for p in m.parameters() if p.requires_grad) == g['n_trainable']
+    from tests.test_oracle_pinned import check_fp
+    for k, p in m.named_parameters():
+        check_fp(p, g['init'][k], rtol=1e-6)
+    torch.manual_seed(g['seed'])
+    o = O.OracleCMUNet(img_size=g['S'], np_seed=g['seed'])
+    o.init_weights()
+    assert list(m.state_dict().keys()) == list(o.state_dict().keys())
+    # state dicts are interchangeable with the oracle/reference layout
+    m.load_state_dict(o.state_dict(), strict=True)
+    assert all(not p.requires_grad for p in m.target_backbone.parameters())
+    assert all(not p.requires_grad for p in m.target_projector.parameters())
+
+
+def test_finetune_unet_keys_pickle_and_loss_names():
+    torch.manual_seed(0)
+    u = C.UNet()
+    torch.manual_seed(0)
+    ou = O.OracleUNet()
+    assert list(u.state_dict().keys()) == list(ou.state_dict().keys())
+    assert all(torch.equal(a, b) for a, b in zip(u.state_dict().values(), ou.state_dict().values()))
+    buf = io.BytesIO()
+    torch.save(u, buf)                      # FT/train.py:212 pickles the whole module
+    buf.seek(0)
+    u2 = torch.load(buf, weights_only=False)
+    assert list(u2.state_dict().keys()) == list(u.state_dict().keys())
+    loss = C.DiceLoss(activation='softmax', threshold=0.5, ignore_channels=[0]) + C.CrossEntropyLoss()
+    assert loss.__name__ == 'dice_loss + cross_entropy_loss'
+    assert C.IoU().__name__ == 'iou_loss'
+    assert (2 * C.CrossEntropyLoss()).__name__ == '2 * cross_entropy_loss'
+    with pytest.raises(ValueError):
+        C.DiceLoss() + 3
+
+
+def test_mode_dispatch_and_upblock_errors():
+    m = C.build(C.cmunet_config(64))
+    with pytest.raises(RuntimeError, match='Invalid mode'):
+        m(torch.zeros(1, 64, 64), mode='predict')
+    with pytest.raises(ValueError):
+        C.UpBlock(8, 4, 'nearest')
+    assert m.momentum == m.base_momentum == 0.996
+
+
+def test_mask_stream_numpy_handover():
+    import numpy as np
+    np.random.seed(60)
+    ms = C.MaskStream()
+    ms.set_numpy_state(np.random.get_state(), device='cpu')
+    st = ms.get_numpy_state()
+    assert st[2] == 624 and (st[1] == np.random.get_state()[1]).all()

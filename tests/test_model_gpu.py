@@ -1,0 +1,76 @@
+"""pytest -m gpu: drop-in modules vs the pinned oracle and the golden values minted from the reference."""
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a B200')
+
+
+def test_pretrain_step_S64_B8_vs_oracle_and_golden():
+    _gpu()
+    from tests import model_checks as M
+    rep = M.pretrain_parity(64, 8, golden=M.golden_pretrain(64, 8))
+    assert not rep['fails'], rep
+
+
+def test_pretrain_step_S224_B4_reference_native_size():
+    _gpu()
+    from tests import model_checks as M
+    rep = M.pretrain_parity(224, 4, golden=M.golden_pretrain(224, 4))
+    assert not rep['fails'], rep
+
+
+def test_pretrain_step_S128_B16():
+    _gpu()
+    from tests import model_checks as M
+    rep = M.pretrain_parity(128, 16, seed=61, data_seed=3)
+    assert not rep['fails'], rep
+
+
+def test_finetune_config1_vs_oracle_and_golden():
+    _gpu()
+    from tests import model_checks as M
+    rep = M.finetune_parity(4, 256, golden=M.golden_finetune())
+    assert not rep['fails'], rep
+    assert rep['name'] == 'dice_loss + cross_entropy_loss'
+
+
+def test_standalone_blocks_accept_fp32_nchw():
+    """DoubleConv / DownBlock / UpBlock work as standalone modules on plain NCHW fp32 tensors."""
+    _gpu()
+    import contrastive_masked_unet_b200 as C
+    from oracle import cmunet_oracle as O
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(5)
+    up = C.UpBlock(128, 64, 'conv_transpose').cuda().train()
+    torch.manual_seed(5)
+    ref = O._Up(128, 64).cuda().train()
+    d = torch.randn(2, 128, 12, 10, device='cuda', requires_grad=True)
+    s = torch.randn(2, 64, 24, 20, device='cuda', requires_grad=True)
+    y = up(d, s)
+    import torch.nn.functional as F
+    yr = O.double_conv_fwd(ref.double_conv, torch.cat([F.conv_transpose2d(d, ref.up_sample.weight, ref.up_sample.bias, stride=2), s], 1))
+    assert y.shape == yr.shape
+    assert (y.float() - yr).abs().max() <= 5e-2 * yr.abs().max()
+    w = torch.linspace(-1, 1, y.numel(), device='cuda').view_as(yr)
+    (y.float() * w).sum().backward()
+    gd, gs = d.grad.clone(), s.grad.clone()
+    d.grad = s.grad = None
+    (yr * w).sum().backward()
+    cos = torch.nn.functional.cosine_similarity
+    assert cos(gd.flatten(), d.grad.flatten(), dim=0) > 0.999
+    assert cos(gs.flatten(), s.grad.flatten(), dim=0) > 0.999
+    with pytest.raises(ValueError):
+        C.UpBlock(8, 4, 'nearest')
+
+
+def test_cpu_tensor_raises_no_fallback():
+    _gpu()
+    import contrastive_masked_unet_b200 as C
+    net = C.UNet().cuda()
+    with pytest.raises(C.CmuError):
+        net(torch.rand(1, 32, 32))
