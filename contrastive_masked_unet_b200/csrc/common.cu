@@ -76,6 +76,7 @@ int num_sms() {
   return n;
 }
 
+unsigned long long g_launch_count = 0;
 static int g_knobs[16] = {0};
 int debug_knob(int key) { return (key >= 0 && key < 16) ? g_knobs[key] : 0; }
 
@@ -86,6 +87,8 @@ extern "C" {
 const char* cmu_last_error(void) { return cmu::last_error().c_str(); }
 
 int cmu_version(void) { return 100; }
+
+long long cmu_launch_count(void) { return (long long)cmu::g_launch_count; }
 
 int cmu_debug_set(int key, int value) {
   if (key < 0 || key >= 16) return cmu::fail("cmu_debug_set: bad key %d", key);

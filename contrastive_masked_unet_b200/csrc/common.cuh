@@ -24,7 +24,13 @@ int fail(const char* fmt, ...);
     if (!(cond)) return ::cmu::fail(__VA_ARGS__); \
   } while (0)
 
-#define CMU_LAUNCH_CHECK() CMU_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro: error check + launch counter (cmu_launch_count)
+extern unsigned long long g_launch_count;
+#define CMU_LAUNCH_CHECK()                 \
+  do {                                     \
+    ++::cmu::g_launch_count;               \
+    CMU_CHECK_CUDA(cudaGetLastError());    \
+  } while (0)
 
 // Encodes a bf16 tiled tensor map with SWIZZLE_128B (inner box = 64 elements = 128 bytes).
 // dims/box are innermost-first; strides_bytes has rank-1 entries (dims 1..rank-1).

@@ -34,6 +34,53 @@ def device_check():
     lib.cmu_device_check()
 
 
+class KernelTimer:
+    """Optional CUDA-event timing of the tensor-core launches (bench.py roofline): set `ops.PROFILER = KernelTimer()`."""
+
+    def __init__(self):
+        self.records = []
+
+    class _Region:
+        def __init__(self, timer, name, flops):
+            self.t, self.name, self.flops = timer, name, flops
+
+        def __enter__(self):
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+        def __exit__(self, *exc):
+            self.e1.record()
+            self.t.records.append((self.name, self.flops, self.e0, self.e1))
+
+    def region(self, name, flops):
+        return KernelTimer._Region(self, name, flops)
+
+    def summarize(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, flops, e0, e1 in self.records:
+            c, ms, fl = out.get(name, (0, 0.0, 0.0))
+            out[name] = (c + 1, ms + e0.elapsed_time(e1), fl + flops)
+        return out
+
+
+class _NoRegion:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+PROFILER = None
+_NOREGION = _NoRegion()
+
+
+def _timed(name, flops):
+    return PROFILER.region(name, flops) if PROFILER is not None else _NOREGION
+
+
 # ------------------------------------------------------------------------------------------- weights
 def pack_conv3x3(w, need_dgrad=True):
     """(Cout,Cin,3,3) fp32 -> (wf [9,Cout,Cin], wd [9,Cin,Cout]) bf16 GEMM operands."""
@@ -88,8 +135,9 @@ def conv3x3_fprop(x0, x1, wf, want_stats=True):
     if want_stats:
         partial = torch.empty(max(lib.cmu_conv_max_grid(), 64) * 2 * max(128, cout), dtype=torch.float32,
                               device=x0.device)
-    lib.cmu_conv3x3_fprop(_ptr(x0), c0, _ptr(x1), c1, n, h, w, _ptr(wf), cout, _ptr(y), _ptr(partial),
-                          ctypes.byref(g), ctypes.byref(b), _stream())
+    with _timed('conv3x3_fprop', 2.0 * n * h * w * cout * 9 * (c0 + c1)):
+        lib.cmu_conv3x3_fprop(_ptr(x0), c0, _ptr(x1), c1, n, h, w, _ptr(wf), cout, _ptr(y), _ptr(partial),
+                              ctypes.byref(g), ctypes.byref(b), _stream())
     if want_stats:
         stats = ConvStats(partial, g.value, b.value, float(n * h * w))
     return y, stats
@@ -101,7 +149,8 @@ def conv3x3_dgrad(dy, wd, c0, c1=0):
     n, h, w, cout = dy.shape
     dx0 = torch.empty(n, h, w, c0, dtype=BF16, device=dy.device)
     dx1 = torch.empty(n, h, w, c1, dtype=BF16, device=dy.device) if c1 else None
-    lib.cmu_conv3x3_dgrad(_ptr(dy), cout, n, h, w, _ptr(wd), _ptr(dx0), c0, _ptr(dx1), c1, _stream())
+    with _timed('conv3x3_dgrad', 2.0 * n * h * w * cout * 9 * (c0 + c1)):
+        lib.cmu_conv3x3_dgrad(_ptr(dy), cout, n, h, w, _ptr(wd), _ptr(dx0), c0, _ptr(dx1), c1, _stream())
     return dx0, dx1
 
 
@@ -115,8 +164,9 @@ def conv3x3_wgrad(x0, x1, dy, dw=None, accumulate=False):
         accumulate = False
     nbytes = lib.cmu_conv3x3_wgrad_workspace_bytes(c0 + c1, cout, n, h, w)
     ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dy.device)
-    lib.cmu_conv3x3_wgrad(_ptr(x0), c0, _ptr(x1), c1, _ptr(dy), cout, n, h, w, _ptr(ws), nbytes, _ptr(dw),
-                          int(accumulate), _stream())
+    with _timed('conv3x3_wgrad', 2.0 * n * h * w * cout * 9 * (c0 + c1)):
+        lib.cmu_conv3x3_wgrad(_ptr(x0), c0, _ptr(x1), c1, _ptr(dy), cout, n, h, w, _ptr(ws), nbytes, _ptr(dw),
+                              int(accumulate), _stream())
     return dw
 
 
@@ -189,7 +239,8 @@ def convT2x2_fprop(x, wf, bias):
     n, h, w, cin = _act(x).shape
     cout = wf.shape[0] // 4
     y = torch.empty(n, 2 * h, 2 * w, cout, dtype=BF16, device=x.device)
-    lib.cmu_convT2x2_fprop(_ptr(x), cin, n, h, w, _ptr(wf), cout, _ptr(bias), _ptr(y), _stream())
+    with _timed('convT_fprop', 2.0 * n * h * w * cin * 4 * cout):
+        lib.cmu_convT2x2_fprop(_ptr(x), cin, n, h, w, _ptr(wf), cout, _ptr(bias), _ptr(y), _stream())
     return y
 
 
@@ -198,7 +249,8 @@ def convT2x2_dgrad(dy, wd):
     cin = wd.shape[0]
     h, w = h2 // 2, w2 // 2
     dx = torch.empty(n, h, w, cin, dtype=BF16, device=dy.device)
-    lib.cmu_convT2x2_dgrad(_ptr(dy), cout, n, h, w, _ptr(wd), cin, _ptr(dx), _stream())
+    with _timed('convT_dgrad', 2.0 * n * h * w * cin * 4 * cout):
+        lib.cmu_convT2x2_dgrad(_ptr(dy), cout, n, h, w, _ptr(wd), cin, _ptr(dx), _stream())
     return dx
 
 
@@ -208,7 +260,8 @@ def convT2x2_wgrad(x, dy):
     dw = torch.empty(cin, cout, 2, 2, dtype=torch.float32, device=x.device)
     nbytes = lib.cmu_convT2x2_wgrad_workspace_bytes(cin, cout, n, h, w)
     ws = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
-    lib.cmu_convT2x2_wgrad(_ptr(x), cin, _ptr(dy), cout, n, h, w, _ptr(ws), nbytes, _ptr(dw), 0, _stream())
+    with _timed('convT_wgrad', 2.0 * n * h * w * cin * 4 * cout):
+        lib.cmu_convT2x2_wgrad(_ptr(x), cin, _ptr(dy), cout, n, h, w, _ptr(ws), nbytes, _ptr(dw), 0, _stream())
     return dw
 
 
@@ -225,7 +278,8 @@ def conv1x1_fprop(x, w_bf16, bias):
     n, h, w, cin = _act(x).shape
     cout = w_bf16.shape[0]
     y = torch.empty(n, h, w, cout, dtype=BF16, device=x.device)
-    lib.cmu_conv1x1_fprop(_ptr(x), cin, n, h, w, _ptr(w_bf16), cout, _ptr(bias), _ptr(y), _stream())
+    with _timed('conv1x1_fprop', 2.0 * n * h * w * cin * cout):
+        lib.cmu_conv1x1_fprop(_ptr(x), cin, n, h, w, _ptr(w_bf16), cout, _ptr(bias), _ptr(y), _stream())
     return y
 
 

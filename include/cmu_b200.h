@@ -25,6 +25,7 @@ extern "C" {
 const char* cmu_last_error(void);
 int cmu_version(void);
 int cmu_device_check(void);               /* current device must be sm_100 */
+long long cmu_launch_count(void);         /* kernels launched by this library so far (this process) */
 int cmu_debug_set(int key, int value);    /* 0: 1 = CUDA-core cross-check path for the conv GEMMs (tests only)
                                              1: 64 = force 64-wide N tiles */
 
