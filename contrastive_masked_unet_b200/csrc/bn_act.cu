@@ -556,13 +556,14 @@ int cmu_bn_bwd_grid(void) { return num_sms() * 4; }
 // sums: [2][C] device buffer receiving (sum dz, sum dz*xhat) == (dbeta, dgamma); partial: [cmu_bn_bwd_grid()][2][C]
 int cmu_bn_relu_bwd(const void* da, const void* dpool, const void* y, const float* scale, const float* shift,
                     const float* mean, const float* rstd, float* partial, float* sums, void* dy, int n, int h, int w,
-                    int c, void* stream) {
+                    int c, int training, void* stream) {
   CMU_REQUIRE(c % 8 == 0 && c / 8 <= 256, "bn_relu_bwd: C must be a multiple of 8 and <= 2048");
   CMU_REQUIRE(da != nullptr || dpool != nullptr, "bn_relu_bwd: no incoming gradient");
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = cmu_bn_bwd_grid();
   const size_t shmem = 2 * (size_t)c * sizeof(float);
-  const float inv_count = 1.f / ((float)n * h * w);
+  // eval-mode BN is a fixed affine map: the batch-statistics terms of the backward vanish
+  const float inv_count = training ? 1.f / ((float)n * h * w) : 0.f;
   const __nv_bfloat16 *pda = (const __nv_bfloat16*)da, *pdp = (const __nv_bfloat16*)dpool, *py = (const __nv_bfloat16*)y;
   if (dpool != nullptr) {
     CMU_REQUIRE(h % 2 == 0 && w % 2 == 0, "bn_relu_bwd: pooling needs even H, W");

@@ -35,10 +35,11 @@ def _nchw_view(a):
 
 
 class BNConfig:
-    __slots__ = ('training', 'momentum', 'eps', 'pool')
+    __slots__ = ('training', 'momentum', 'eps', 'pool', 'grad')
 
     def __init__(self, training, momentum, eps, pool):
         self.training, self.momentum, self.eps, self.pool = training, momentum, eps, pool
+        self.grad = torch.is_grad_enabled()     # captured at call time (grad mode is always off inside Function.forward)
 
 
 class ConvBNReLUFn(torch.autograd.Function):
@@ -49,19 +50,17 @@ class ConvBNReLUFn(torch.autograd.Function):
     def forward(ctx, x0, x1, weight, bias, gamma, beta, running_mean, running_var, cfg):
         a0 = _nhwc(x0)
         a1 = _nhwc(x1) if x1 is not None else None
-        need_grad = any(ctx.needs_input_grad)
+        need_grad = cfg.grad and any(ctx.needs_input_grad)
         wf, wd = ops.pack_conv3x3(weight, need_dgrad=need_grad)
         y, stats = ops.conv3x3_fprop(a0, a1, wf, want_stats=cfg.training)
         scale, shift, mean, rstd = ops.bn_finalize(stats, gamma, beta, bias, running_mean, running_var, cfg.momentum,
                                                    cfg.eps, cfg.training)
         act, pooled = ops.bn_relu_apply(y, scale, shift, cfg.pool)
         if need_grad:
-            if not cfg.training:
-                raise CmuError('backward through eval-mode BatchNorm is not implemented (train() the module)')
             ctx.save_for_backward(a0, a1, y, scale, shift, mean, rstd, wd)
             ctx.c0 = a0.shape[3]
             ctx.c1 = 0 if a1 is None else a1.shape[3]
-        ctx.pool = cfg.pool
+        ctx.pool, ctx.bn_training = cfg.pool, cfg.training
         if cfg.pool:
             return _nchw_view(act), _nchw_view(pooled)
         return _nchw_view(act)
@@ -75,7 +74,7 @@ class ConvBNReLUFn(torch.autograd.Function):
             return (None,) * 9
         if da is None and not ctx.pool:
             return (None,) * 9
-        dy, dgamma, dbeta = ops.bn_relu_bwd(da, dp, y, scale, shift, mean, rstd)
+        dy, dgamma, dbeta = ops.bn_relu_bwd(da, dp, y, scale, shift, mean, rstd, ctx.bn_training)
         dx0 = dx1 = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             g0, g1 = ops.conv3x3_dgrad(dy, wd, ctx.c0, ctx.c1)
@@ -97,17 +96,16 @@ class FirstConvBNReLUFn(torch.autograd.Function):
         scale, shift, mean, rstd = ops.bn_finalize(stats, gamma, beta, bias, running_mean, running_var, cfg.momentum,
                                                    cfg.eps, cfg.training)
         act, _ = ops.bn_relu_apply(y, scale, shift, False)
-        if any(ctx.needs_input_grad):
-            if not cfg.training:
-                raise CmuError('backward through eval-mode BatchNorm is not implemented (train() the module)')
+        if cfg.grad and any(ctx.needs_input_grad):
             ctx.save_for_backward(x, mask, y, scale, shift, mean, rstd)
+        ctx.bn_training = cfg.training
         return _nchw_view(act)
 
     @staticmethod
     def backward(ctx, d_act):
         x, mask, y, scale, shift, mean, rstd = ctx.saved_tensors
         da = _nhwc(to_act(d_act))
-        dy, dgamma, dbeta = ops.bn_relu_bwd(da, None, y, scale, shift, mean, rstd)
+        dy, dgamma, dbeta = ops.bn_relu_bwd(da, None, y, scale, shift, mean, rstd, ctx.bn_training)
         dw = ops.conv3x3_c1_wgrad(x, mask, dy) if ctx.needs_input_grad[2] else None
         dbias = torch.zeros(dy.shape[3], dtype=torch.float32, device=dy.device) if ctx.needs_input_grad[3] else None
         # the input image never needs a gradient on this path (f1 "not needed")

@@ -222,7 +222,7 @@ def bn_relu_apply(y, scale, shift, pool=False):
     return a, pooled
 
 
-def bn_relu_bwd(da, dpool, y, scale, shift, mean, rstd):
+def bn_relu_bwd(da, dpool, y, scale, shift, mean, rstd, training=True):
     """-> (dy act, dgamma (C,), dbeta (C,))."""
     n, h, w, c = _act(y).shape
     grid = lib.cmu_bn_bwd_grid()
@@ -230,7 +230,7 @@ def bn_relu_bwd(da, dpool, y, scale, shift, mean, rstd):
     sums = torch.empty(2, c, dtype=torch.float32, device=y.device)
     dy = torch.empty_like(y)
     lib.cmu_bn_relu_bwd(_ptr(da), _ptr(dpool), _ptr(y), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd),
-                        _ptr(partial), _ptr(sums), _ptr(dy), n, h, w, c, _stream())
+                        _ptr(partial), _ptr(sums), _ptr(dy), n, h, w, c, int(training), _stream())
     return dy, sums[1], sums[0]
 
 

@@ -80,7 +80,7 @@ int cmu_bn_relu_apply(const void* y, const float* scale, const float* shift, voi
 int cmu_bn_bwd_grid(void);
 int cmu_bn_relu_bwd(const void* da, const void* dpool, const void* y, const float* scale, const float* shift,
                     const float* mean, const float* rstd, float* partial /* float[grid][2][C] */, float* sums, void* dy,
-                    int n, int h, int w, int c, void* stream);
+                    int n, int h, int w, int c, int training, void* stream);
 
 /* ---- a5  UpBlock pieces: CMU/necks/munet_neck.py:25-49 == FT/model.py:57-81 ------------------------------ */
 int cmu_convT2x2_fprop(const void* x, int cin, int n, int h, int w, const void* w_packed, int cout, const float* bias,

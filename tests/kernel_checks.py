@@ -205,7 +205,7 @@ def check_head1x1(n=2, h=20, w=28, seed=4):
     torch.cuda.synchronize()
     res = {'fwd': rel_err(y, yr.detach()), 'da': rel_err(nchw(da), ar.grad), 'dw': rel_err(dw, wr.grad.view(2, 64)),
            'db': rel_err(db, br.grad)}
-    assert res['fwd'] < 1e-5 and res['da'] < 1e-2 and res['dw'] < 1e-4 and res['db'] < 1e-4, res
+    assert res['fwd'] < 1e-4 and res['da'] < 1e-2 and res['dw'] < 1e-4 and res['db'] < 1e-4, res
     return res
 
 

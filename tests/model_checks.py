@@ -131,7 +131,9 @@ def pretrain_parity(S=64, B=8, seed=60, data_seed=1, golden=None, grad_cos=0.999
         cos_table[k] = c
         if c < worst[0]:
             worst = (c, k)
-        need = min(grad_cos, ac[k] - margin) if k in ac else grad_cos
+        # ill-conditioned sums (e.g. ConvTranspose biases: heavy cancellation) where even torch's bf16 run is < 0.9
+        # get a wider band
+        need = min(grad_cos, ac[k] - (margin if ac[k] >= 0.9 else 0.2)) if k in ac else grad_cos
         if c < need:
             fails.append(f'{k}: grad cosine {c:.6f} < {need:.6f} (torch bf16 autocast: {ac.get(k)}; |g| oracle {gn:.3e})')
     rep['worst_grad_cos'] = worst

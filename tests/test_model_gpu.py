@@ -62,8 +62,9 @@ def test_standalone_blocks_accept_fp32_nchw():
     d.grad = s.grad = None
     (yr * w).sum().backward()
     cos = torch.nn.functional.cosine_similarity
-    assert cos(gd.flatten(), d.grad.flatten(), dim=0) > 0.999
-    assert cos(gs.flatten(), s.grad.flatten(), dim=0) > 0.999
+    # the fp32 inputs are quantised to bf16 at the module boundary, hence 0.995 here (kernel-level checks: > 0.9999)
+    assert cos(gd.flatten(), d.grad.flatten(), dim=0) > 0.995
+    assert cos(gs.flatten(), s.grad.flatten(), dim=0) > 0.995
     with pytest.raises(ValueError):
         C.UpBlock(8, 4, 'nearest')
 
