@@ -71,20 +71,64 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
     y[i] = __float2bfloat16_rn(x[i]);
 }
 
+// fp32 (R, C) row-major -> bf16 (C, R) row-major through a 64x64 shared-memory tile (both sides coalesced);
+// optionally also writes the untransposed bf16 copy (same read of x).
+__global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ yt,
+                                                             __nv_bfloat16* __restrict__ y, long long R, long long C) {
+  __shared__ float tile[64][65];
+  const long long r0 = (long long)blockIdx.y * 64, c0 = (long long)blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+  for (int i = ty; i < 64; i += 4) {
+    const long long r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = x[r * C + c];
+      if (y != nullptr) y[r * C + c] = __float2bfloat16_rn(v);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 4) {
+    const long long c = c0 + i, r = r0 + tx;
+    if (r < R && c < C) yt[c * R + r] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+
 // ---------------------------------------------------------------------------------- first conv (Cin = 1)
 // y[n,h,w,co] = sum_{r,s} w[co][r][s] * (x[n,h+r-1,w+s-1] * (1 - mask0[h+r-1,w+s-1]))     (Q1: image-0 mask)
-// 8 threads per pixel, 8 channels each (Cout = 64).  Per-channel sum / sum-of-squares are accumulated in registers
-// over a grid-stride loop and reduced per block -> stats_partial[block][2][64].
+// Persistent blocks walk image rows (n,h); the three masked input rows are staged once in shared memory (with a
+// zero halo column on both sides), then 8 threads per pixel produce 8 channels each (Cout = 64) and write one
+// coalesced 128-byte NHWC row.  Per-channel sum / sum-of-squares stay in registers across rows and are reduced per
+// block -> stats_partial[block][2][64].  No 64-bit div/mod in the inner loop.
 constexpr int kC1Cout = 64;
+constexpr int kC1MaxW = 2048;
+
+__device__ __forceinline__ void c1_stage_rows(float (*srow)[kC1MaxW + 2], const float* __restrict__ x,
+                                              const uint8_t* __restrict__ mask0, int nb, int h, int H, int W) {
+  for (int i = threadIdx.x; i < 3 * (W + 2); i += blockDim.x) {
+    const int r = i / (W + 2), c = i - r * (W + 2);
+    const int hh = h + r - 1, ww = c - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+      v = __ldg(x + ((size_t)nb * H + hh) * W + ww);
+      if (mask0 != nullptr && mask0[hh * W + ww]) v = 0.f;
+    }
+    srow[r][c] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256) conv_c1_fprop_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask0,
                                                             const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
                                                             float* __restrict__ stats_partial, int N, int H, int W) {
+  extern __shared__ float c1_smem[];
+  float (*srow)[kC1MaxW + 2] = reinterpret_cast<float (*)[kC1MaxW + 2]>(c1_smem);
   __shared__ float sw[kC1Cout * 9];
   __shared__ float sred[2][kC1Cout];
   for (int i = threadIdx.x; i < kC1Cout * 9; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < 2 * kC1Cout; i += blockDim.x) (&sred[0][0])[i] = 0.f;
   __syncthreads();
-  const int cg = threadIdx.x & 7;  // channel group: channels cg*8 .. cg*8+7
+  const int cg = threadIdx.x & 7;   // channel group: channels cg*8 .. cg*8+7
+  const int px = threadIdx.x >> 3;  // 32 pixels per pass
   float wr[8][9];
 #pragma unroll
   for (int c = 0; c < 8; ++c)
@@ -93,42 +137,39 @@ __global__ void __launch_bounds__(256) conv_c1_fprop_kernel(const float* __restr
   float s1[8], s2[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) s1[c] = s2[c] = 0.f;
-  const size_t npix = (size_t)N * H * W;
-  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < npix;
-       pix += ((size_t)gridDim.x * blockDim.x) >> 3) {
-    const int wq = pix % W;
-    const int hq = (pix / W) % H;
-    const size_t nb = pix / ((size_t)W * H);
-    float xin[9];
+  const int rows = N * H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int nb = row / H, h = row - nb * H;
+    __syncthreads();
+    c1_stage_rows(srow, x, mask0, nb, h, H, W);
+    __syncthreads();
+    uint4* yrow = reinterpret_cast<uint4*>(y) + (size_t)row * W * 8;
+    for (int w0 = 0; w0 < W; w0 += 32) {
+      const int wq = w0 + px;
+      if (wq < W) {
+        float xin[9];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int hh = hq + r - 1, ww = wq + s - 1;
-        float v = 0.f;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-          v = __ldg(x + (nb * H + hh) * W + ww);
-          if (mask0 != nullptr && mask0[hh * W + ww]) v = 0.f;
+          for (int s = 0; s < 3; ++s) xin[r * 3 + s] = srow[r][wq + s];
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float a = 0.f;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) a = fmaf(wr[c][t], xin[t], a);
+          o[c] = a;
+          s1[c] += a;
+          s2[c] += a * a;
         }
-        xin[r * 3 + s] = v;
+        yrow[wq * 8 + cg] = pack8(o);
       }
-    float o[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float a = 0.f;
-#pragma unroll
-      for (int t = 0; t < 9; ++t) a = fmaf(wr[c][t], xin[t], a);
-      o[c] = a;
-      s1[c] += a;
-      s2[c] += a * a;
     }
-    reinterpret_cast<uint4*>(y)[pix * 8 + cg] = pack8(o);
   }
   if (stats_partial != nullptr) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      // lanes with equal cg: xor-reduce over lane bits 3,4
-      float a = s1[c], b = s2[c];
+      float a = s1[c], b = s2[c];   // lanes with equal cg: xor-reduce over lane bits 3,4
       a += __shfl_xor_sync(0xffffffffu, a, 8);
       a += __shfl_xor_sync(0xffffffffu, a, 16);
       b += __shfl_xor_sync(0xffffffffu, b, 8);
@@ -148,41 +189,42 @@ __global__ void __launch_bounds__(256) conv_c1_fprop_kernel(const float* __restr
 __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask0,
                                                             const __nv_bfloat16* __restrict__ dy, float* __restrict__ partial,
                                                             int N, int H, int W) {
+  extern __shared__ float c1_smem[];
+  float (*srow)[kC1MaxW + 2] = reinterpret_cast<float (*)[kC1MaxW + 2]>(c1_smem);
   __shared__ float sred[kC1Cout * 9];
   for (int i = threadIdx.x; i < kC1Cout * 9; i += blockDim.x) sred[i] = 0.f;
-  __syncthreads();
   const int cg = threadIdx.x & 7;
+  const int px = threadIdx.x >> 3;
   float acc[8][9];
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
-  const size_t npix = (size_t)N * H * W;
-  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < npix;
-       pix += ((size_t)gridDim.x * blockDim.x) >> 3) {
-    const int wq = pix % W;
-    const int hq = (pix / W) % H;
-    const size_t nb = pix / ((size_t)W * H);
-    float xin[9];
+  const int rows = N * H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int nb = row / H, h = row - nb * H;
+    __syncthreads();
+    c1_stage_rows(srow, x, mask0, nb, h, H, W);
+    __syncthreads();
+    const uint4* grow = reinterpret_cast<const uint4*>(dy) + (size_t)row * W * 8;
+    for (int w0 = 0; w0 < W; w0 += 32) {
+      const int wq = w0 + px;
+      if (wq < W) {
+        float xin[9];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int hh = hq + r - 1, ww = wq + s - 1;
-        float v = 0.f;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
-          v = __ldg(x + (nb * H + hh) * W + ww);
-          if (mask0 != nullptr && mask0[hh * W + ww]) v = 0.f;
-        }
-        xin[r * 3 + s] = v;
+          for (int s = 0; s < 3; ++s) xin[r * 3 + s] = srow[r][wq + s];
+        float g[8];
+        unpack8(grow[wq * 8 + cg], g);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], xin[t], acc[c][t]);
       }
-    float g[8];
-    unpack8(reinterpret_cast<const uint4*>(dy)[pix * 8 + cg], g);
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-#pragma unroll
-      for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], xin[t], acc[c][t]);
+    }
   }
+  __syncthreads();
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
@@ -488,13 +530,23 @@ int cmu_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream) {
   return 0;
 }
 
-int cmu_conv3x3_c1_grid(void) { return num_sms() * 4; }
+int cmu_transpose_cast_bf16(const float* x, void* yt, void* y, long long rows, long long cols, void* stream) {
+  dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64));
+  CMU_REQUIRE(grid.y <= 65535, "transpose_cast: too many rows (%lld)", rows);
+  transpose_cast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)yt, (__nv_bfloat16*)y, rows, cols);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_conv3x3_c1_grid(void) { return num_sms() * 6; }
 
 int cmu_conv3x3_c1_fprop(const float* x, const unsigned char* mask0, const float* w, int cout, void* y,
                          float* stats_partial, int n, int h, int wd, void* stream) {
   CMU_REQUIRE(cout == kC1Cout, "conv3x3_c1: Cout must be 64 (got %d)", cout);
-  conv_c1_fprop_kernel<<<cmu_conv3x3_c1_grid(), 256, 0, (cudaStream_t)stream>>>(x, mask0, w, (__nv_bfloat16*)y,
-                                                                               stats_partial, n, h, wd);
+  CMU_REQUIRE(wd <= kC1MaxW, "conv3x3_c1: image width %d exceeds %d", wd, kC1MaxW);
+  const int c1_shmem = 3 * (kC1MaxW + 2) * (int)sizeof(float);
+  conv_c1_fprop_kernel<<<cmu_conv3x3_c1_grid(), 256, c1_shmem, (cudaStream_t)stream>>>(x, mask0, w, (__nv_bfloat16*)y,
+                                                                                      stats_partial, n, h, wd);
   CMU_LAUNCH_CHECK();
   return 0;
 }
@@ -503,7 +555,9 @@ int cmu_conv3x3_c1_wgrad(const float* x, const unsigned char* mask0, const void*
                          int accumulate, int n, int h, int wd, void* stream) {
   CMU_REQUIRE(cout == kC1Cout, "conv3x3_c1: Cout must be 64 (got %d)", cout);
   const int grid = cmu_conv3x3_c1_grid();
-  conv_c1_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, mask0, (const __nv_bfloat16*)dy, partial, n, h, wd);
+  CMU_REQUIRE(wd <= kC1MaxW, "conv3x3_c1: image width %d exceeds %d", wd, kC1MaxW);
+  const int c1_shmem = 3 * (kC1MaxW + 2) * (int)sizeof(float);
+  conv_c1_wgrad_kernel<<<grid, 256, c1_shmem, (cudaStream_t)stream>>>(x, mask0, (const __nv_bfloat16*)dy, partial, n, h, wd);
   CMU_LAUNCH_CHECK();
   reduce_rows_kernel<<<ceil_div(kC1Cout * 9, 128), 128, 0, (cudaStream_t)stream>>>(partial, dw, grid, kC1Cout * 9,
                                                                                    accumulate);

@@ -24,7 +24,7 @@ constexpr int kK2Smem = kK2Stages * kK2Stage + 1024 + 512;
 
 struct K2Params {
   CUtensorMap tmP, tmQ0, tmQ1;
-  int mode;            // 0 = conv3x3 wgrad, 1 = convT2x2 wgrad
+  int mode;            // 0 = conv3x3 wgrad, 1 = convT2x2 wgrad, 2 = plain rows (D = Q^T P over matrix rows)
   int N, H, W;         // pixel space
   int q0, q1;          // channels of Q source 0 / 1
   int pc;              // channels of P
@@ -102,8 +102,10 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
             const bool second = qc >= p.q0;
             tma_load_4d(sQ + a * kQAtom, second ? &p.tmQ1 : &p.tmQ0, &full_bar[st], second ? qc - p.q0 : qc,
                         w0 + g - 1, h0 - 1, img);
-          } else {
+          } else if (p.mode == 1) {
             tma_load_5d(sQ + a * kQAtom, &p.tmQ0, &full_bar[st], (g & 1) * p.q0 + qc, w0, g >> 1, h0, img);
+          } else {
+            tma_load_4d(sQ + a * kQAtom, &p.tmQ0, &full_bar[st], qc, w0, h0, img);
           }
         }
         for (int a = 0; a < n_atoms; ++a)
@@ -205,6 +207,17 @@ __global__ void wgrad_reduce_convT(const float* __restrict__ ws, float* __restri
   *o = accumulate ? *o + acc : acc;
 }
 
+// out[m][n] (+)= sum_split ws[split][m][n] (+ bias[n])        (plain rows mode)
+__global__ void rows_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int total, int pc, int splits,
+                                   const float* __restrict__ bias, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  float acc = 0.f;
+  for (int sp = 0; sp < splits; ++sp) acc += ws[(size_t)sp * total + idx];
+  if (bias != nullptr) acc += bias[idx % pc];
+  out[idx] = accumulate ? out[idx] + acc : acc;
+}
+
 static int make_act_map4(CUtensorMap* m, const void* base, int N, int H, int W, int C, int box_w, int box_h) {
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
   uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
@@ -243,7 +256,7 @@ static void plan_k2(int mode, int N, int H, int W, int qc, int pc, K2Plan* pl) {
   pl->MT = ceil_div(qc, 128);
   pl->n_cols = (pc % 128 == 0) ? 128 : 64;
   pl->NT = pc / pl->n_cols;
-  pl->G = (mode == 0) ? 3 : 4;
+  pl->G = (mode == 0) ? 3 : (mode == 1 ? 4 : 1);
   pl->taps = (mode == 0) ? 3 : 1;
   const int base = pl->MT * pl->NT * pl->G;
   int splits = num_sms() / base;
@@ -256,8 +269,9 @@ int simt_wgrad(int mode, const void* x0, int c0, const void* x1, int c1, const v
                float* dw, int accumulate, cudaStream_t st);
 
 static int run_k2(int mode, const void* q0, int qc0, const void* q1, int qc1, const void* pten, int pc, int N, int H,
-                  int W, float* ws, size_t ws_bytes, float* dw, int accumulate, cudaStream_t stream) {
-  if (debug_knob(0) == 1) {  // CUDA-core cross-check path (tests / debugging only)
+                  int W, float* ws, size_t ws_bytes, float* dw, int accumulate, cudaStream_t stream,
+                  const float* bias = nullptr) {
+  if (debug_knob(0) == 1 && mode != 2) {  // CUDA-core cross-check path (tests / debugging only)
     if (mode == 0) return simt_wgrad(0, q0, qc0, q1, qc1, pten, pc, N, H, W, dw, accumulate, stream);
     return simt_wgrad(1, pten, pc, nullptr, 0, q0, qc0, N, H, W, dw, accumulate, stream);
   }
@@ -266,7 +280,9 @@ static int run_k2(int mode, const void* q0, int qc0, const void* q1, int qc1, co
   K2Plan pl;
   plan_k2(mode, N, H, W, qc, pc, &pl);
   const size_t need = (size_t)pl.splits * pl.G * pl.taps * qc * pc * sizeof(float);
-  CMU_REQUIRE(ws != nullptr && ws_bytes >= need, "wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
+  const bool direct = (mode == 2 && pl.splits == 1 && bias == nullptr && !accumulate);   // D already has the output layout
+  if (direct) ws = dw;
+  CMU_REQUIRE(direct || (ws != nullptr && ws_bytes >= need), "wgrad: workspace too small (%zu < %zu)", ws_bytes, need);
   K2Params p;
   memset(&p, 0, sizeof(p));
   p.mode = mode;
@@ -284,8 +300,11 @@ static int run_k2(int mode, const void* q0, int qc0, const void* q1, int qc1, co
     } else {
       p.tmQ1 = p.tmQ0;
     }
-  } else {
+  } else if (mode == 1) {
     if (make_up_map5(&p.tmQ0, q0, N, H, W, qc0, pl.TW, pl.TH)) return 1;
+    p.tmQ1 = p.tmQ0;
+  } else {
+    if (make_act_map4(&p.tmQ0, q0, N, H, W, qc0, pl.TW, pl.TH)) return 1;
     p.tmQ1 = p.tmQ0;
   }
   static bool attr_set = false;
@@ -299,9 +318,11 @@ static int run_k2(int mode, const void* q0, int qc0, const void* q1, int qc1, co
   const int total = pl.G * pl.taps * qc * pc;
   if (mode == 0)
     wgrad_reduce_conv3<<<ceil_div(total, 256), 256, 0, stream>>>(ws, dw, qc, pc, pl.splits, accumulate);
-  else
+  else if (mode == 1)
     wgrad_reduce_convT<<<ceil_div(total, 256), 256, 0, stream>>>(ws, dw, pc, qc, pl.splits, accumulate);
-  CMU_LAUNCH_CHECK();
+  else if (!direct)
+    rows_reduce_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(ws, dw, total, pc, pl.splits, bias, accumulate);
+  if (mode != 2 || !direct) CMU_LAUNCH_CHECK();
   return 0;
 }
 
@@ -327,6 +348,22 @@ long long cmu_convT2x2_wgrad_workspace_bytes(int cin, int cout, int n, int h, in
   K2Plan pl;
   plan_k2(1, n, h, w, cout, cin, &pl);
   return (long long)pl.splits * 4 * cin * cout * 4;
+}
+
+// D[qc][pc] = Q^T P over `rows` matrix rows: Q (rows, qc) bf16, P (rows, pc) bf16, out (qc, pc) fp32 (+ bias[pc]).
+// Used for the projection-head linears (nonlinear_neck.py:94): forward, dgrad and wgrad are all of this form once the
+// small operand is transposed.  qc, pc multiples of 64; rows arbitrary (zero-filled to 128-row tiles by TMA).
+long long cmu_gemm_tn_workspace_bytes(int qc, int pc, long long rows) {
+  K2Plan pl;
+  plan_k2(2, 1, 1, (int)rows, qc, pc, &pl);
+  return pl.splits > 1 ? (long long)pl.splits * qc * pc * 4 : 0;
+}
+
+int cmu_gemm_tn_bf16(const void* q, int qc, const void* p, int pc, long long rows, float* out, const float* bias,
+                     int accumulate, float* workspace, long long workspace_bytes, void* stream) {
+  CMU_REQUIRE(rows > 0 && rows < (1ll << 31), "gemm_tn: bad row count");
+  return run_k2(2, q, qc, nullptr, 0, p, pc, 1, 1, (int)rows, workspace, (size_t)workspace_bytes, out, accumulate,
+                (cudaStream_t)stream, bias);
 }
 
 int cmu_convT2x2_wgrad(const void* x, int cin, const void* dy, int cout, int n, int h, int w, float* workspace,

@@ -178,14 +178,27 @@ class ChannelMean2Fn(torch.autograd.Function):
 
 
 class LinearFn(torch.autograd.Function):
-    """nn.Linear on a (M,K) fp32 matrix (nonlinear_neck.py:94,99)."""
+    """nn.Linear on a (M,K) fp32 matrix (nonlinear_neck.py:94,99).  Large layers (projector.fc0: K = S*S) run on the
+    tcgen05 engine in bf16 with fp32 accumulation: y = (x^T)^T W^T, dx = (dy^T)^T W, dW = dy^T x are all "reduce over
+    matrix rows" GEMMs once the small operand is transposed; small layers use the fp32 SIMT SGEMM."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         x = x.contiguous().float()
         w = weight.detach().contiguous().float()
-        y = ops.linear_fwd(x, w, bias.detach().contiguous().float() if bias is not None else None)
-        ctx.save_for_backward(x, w)
+        m, k = x.shape
+        n = w.shape[0]
+        b = bias.detach().contiguous().float() if bias is not None else None
+        ctx.tc = ops.tc_linear_ok(m, k, n)
+        if ctx.tc:
+            need_dx = ctx.needs_input_grad[0]
+            wt16, w16 = ops.transpose_cast(w, also_plain=need_dx)          # (K,N) [, (N,K)] bf16
+            xt16, x16 = ops.transpose_cast(x, also_plain=ctx.needs_input_grad[1])   # (K,M) [, (M,K)]
+            y = ops.gemm_tn(xt16, wt16, bias=b)                            # (M,N) = x W^T + b
+            ctx.save_for_backward(x16, w16)
+        else:
+            y = ops.linear_fwd(x, w, b)
+            ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
         return y
 
@@ -193,8 +206,16 @@ class LinearFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dy = dy.contiguous().float()
-        dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
-        dw = ops.linear_wgrad(dy, x) if ctx.needs_input_grad[1] else None
+        dx = dw = None
+        if ctx.tc:
+            dyt16, dy16 = ops.transpose_cast(dy, also_plain=True)          # (N,M), (M,N) bf16
+            if ctx.needs_input_grad[0]:
+                dx = ops.gemm_tn(dyt16, w)                                 # (M,K) = dy W
+            if ctx.needs_input_grad[1]:
+                dw = ops.gemm_tn(dy16, x)                                  # (N,K) = dy^T x
+        else:
+            dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
+            dw = ops.linear_wgrad(dy, x) if ctx.needs_input_grad[1] else None
         db = ops.colsum(dy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx, dw, db
 

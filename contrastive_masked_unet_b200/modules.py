@@ -40,10 +40,18 @@ class MaskStream:
     """Device-resident MT19937 stream that continues numpy's legacy global RNG bit-for-bit
     (UNet_encoder.py:124 `np.random.shuffle`).  By default it is seeded lazily from `np.random.get_state()` at first
     use, so `np.random.seed(s)` before training gives the reference's masks (quirk Q2: online and target encoders
-    share ONE stream, online first)."""
+    share ONE stream, online first).
+
+    pair_mode (set by CM_UNet): the stream is inherently sequential, so after the (online, target) pair of step t has
+    been served the pair of step t+1 is generated on a side CUDA stream while step t computes -- same draws, same
+    order, off the critical path.  A changed batch/size rolls the state back and regenerates synchronously."""
 
     def __init__(self):
         self.state = None
+        self.pair_mode = False
+        self._pref = None            # (key, mask, event, state_backup)
+        self._target_served = None   # key of a prefetched pair whose target half is still to be "drawn"
+        self._side = None
 
     def _ensure(self, device):
         if self.state is None:
@@ -52,28 +60,98 @@ class MaskStream:
             self.state = self.state.to(device)
 
     def seed(self, seed, device='cuda'):
+        self._drop_prefetch()
         self.state = torch.empty(lib.cmu_mask_state_words(), dtype=torch.int32, device=device)
         lib.cmu_mask_seed(self.state.data_ptr(), int(seed) & 0xFFFFFFFF, ops._stream())
 
     def set_numpy_state(self, np_state, device='cuda'):
         assert np_state[0] == 'MT19937'
+        self._drop_prefetch()
         words = np.concatenate([np.asarray(np_state[1], dtype=np.uint32), np.array([np_state[2]], dtype=np.uint32)])
         self.state = torch.from_numpy(words.view(np.int32).copy()).to(device)
 
     def get_numpy_state(self):
-        w = self.state.cpu().numpy().view(np.uint32)
+        """Logical position of the stream (a prefetched, not yet consumed pair does not count)."""
+        st = self.state
+        if self._pref is not None:
+            self._pref[2].synchronize()
+            st = self._pref[3]
+        w = st.cpu().numpy().view(np.uint32)
         return ('MT19937', w[:624].copy(), int(w[624]), 0, 0.0)
 
-    def generate(self, batch, img_size, patch_size, mask_ratio, device):
-        """One `create_random_patch_mask` call: consumes `batch` shuffles, returns the (B,S,S) uint8 mask."""
-        self._ensure(device)
+    def _drop_prefetch(self):
+        if self._pref is not None:
+            _, _, ev, backup = self._pref
+            torch.cuda.current_stream().wait_event(ev)
+            self.state.copy_(backup)          # roll the stream back to its logical position
+            self._pref = None
+        self._target_served = None
+
+    @staticmethod
+    def _k(img_size, patch_size, mask_ratio):
         g = img_size // patch_size
-        k = min(int(mask_ratio * img_size * img_size) // (patch_size * patch_size), g * g)
+        return min(int(mask_ratio * img_size * img_size) // (patch_size * patch_size), g * g)
+
+    def _launch(self, batch, img_size, patch_size, k, n_shuffles, device):
         mask = torch.empty(batch, img_size, img_size, dtype=torch.uint8, device=device)
         ws = torch.empty(max(batch * k, 1), dtype=torch.int32, device=device)
-        lib.cmu_mask_generate(self.state.data_ptr(), mask.data_ptr(), ws.data_ptr(), batch, img_size, patch_size, k, batch,
-                              ops._stream())
-        return mask, k
+        lib.cmu_mask_generate(self.state.data_ptr(), mask.data_ptr(), ws.data_ptr(), batch, img_size, patch_size, k,
+                              n_shuffles, ops._stream())
+        return mask
+
+    def _prefetch(self, key, device):
+        batch, img_size, patch_size, k = key
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=device)
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            backup = self.state.clone()
+            mask = self._launch(batch, img_size, patch_size, k, 2 * batch, device)   # online half kept + target draws
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+        self._pref = (key, mask, ev, backup)
+
+    def generate(self, batch, img_size, patch_size, mask_ratio, device):
+        """One `create_random_patch_mask` call: consumes `batch` shuffles, returns ((B,S,S) uint8 mask, K)."""
+        self._ensure(device)
+        k = self._k(img_size, patch_size, mask_ratio)
+        if not self.pair_mode:
+            return self._launch(batch, img_size, patch_size, k, batch, device), k
+        if k > 0:                                             # online call
+            key = (batch, img_size, patch_size, k)
+            if self._pref is not None and self._pref[0] == key:
+                _, mask, ev, _ = self._pref
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ev)
+                mask.record_stream(cur)
+                self._pref = None
+                self._target_served = key[:3]
+                self._last_key = key
+                return mask, k
+            self._drop_prefetch()
+            self._last_key = key
+            return self._launch(batch, img_size, patch_size, k, batch, device), k
+        # target call (mask_ratio 0): B shuffles are drawn and discarded (Q2)
+        tkey = (batch, img_size, patch_size)
+        if self._target_served == tkey:
+            self._target_served = None                        # already drawn by the prefetched pair
+            mask = torch.zeros(batch, img_size, img_size, dtype=torch.uint8, device=device)
+        else:
+            self._drop_prefetch()
+            mask = self._launch(batch, img_size, patch_size, 0, batch, device)
+        nxt = self._last_key
+        if nxt is not None and nxt[:3] == tkey:
+            self._prefetch(nxt, device)                       # pair of the next step, on the side stream
+        return mask, 0
+
+    _last_key = None
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        if d.get('_pref') is not None:
+            d['state'] = d['_pref'][3]
+        d['_pref'] = d['_side'] = d['_target_served'] = None
+        return d
 
 
 # --------------------------------------------------------------------------------------------------------- conv blocks
@@ -384,6 +462,7 @@ class CM_UNet(nn.Module):
             p.requires_grad = False
         # one numpy-compatible mask stream shared by both encoders, online first (quirk Q2)
         self.target_backbone.mask_stream = self.backbone.mask_stream
+        self.backbone.mask_stream.pair_mode = True
         # Q3: the reference draws a fresh, untrained Conv2d(1024,256,1) in every forward_train (cmunet.py:128).
         # persistent_reduce=True (opt-in) keeps the first draw.
         self.persistent_reduce = persistent_reduce

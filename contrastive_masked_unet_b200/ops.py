@@ -337,6 +337,37 @@ def linear_wgrad(dy, x):
     return sgemm(dy, 1, n, x, 1, k, n, k, m)
 
 
+def transpose_cast(x, also_plain=False):
+    """fp32 (R,C) -> bf16 (C,R) [and optionally the untransposed bf16 (R,C)] in one pass over x."""
+    x = x.detach().contiguous().float()
+    r, c = x.shape
+    yt = torch.empty(c, r, dtype=BF16, device=x.device)
+    y = torch.empty(r, c, dtype=BF16, device=x.device) if also_plain else None
+    lib.cmu_transpose_cast_bf16(_ptr(x), _ptr(yt), _ptr(y), r, c, _stream())
+    return yt, y
+
+
+def gemm_tn(q, p, bias=None, out=None, accumulate=False):
+    """out (QC,PC) fp32 = q^T p (+ bias[PC]); q (R,QC) bf16, p (R,PC) bf16 -- tcgen05 (K2 engine, rows = reduction)."""
+    assert q.dtype == BF16 and p.dtype == BF16 and q.is_contiguous() and p.is_contiguous() and q.shape[0] == p.shape[0]
+    rows, qc = q.shape
+    pc = p.shape[1]
+    if out is None:
+        out = torch.empty(qc, pc, dtype=torch.float32, device=q.device)
+        accumulate = False
+    nbytes = lib.cmu_gemm_tn_workspace_bytes(qc, pc, rows)
+    ws = torch.empty(nbytes // 4, dtype=torch.float32, device=q.device) if nbytes else None
+    with _timed('gemm_tn', 2.0 * rows * qc * pc):
+        lib.cmu_gemm_tn_bf16(_ptr(q), qc, _ptr(p), pc, rows, _ptr(out), _ptr(bias), int(accumulate), _ptr(ws), nbytes,
+                             _stream())
+    return out
+
+
+def tc_linear_ok(m, k, n):
+    """Shapes for which the projector linears run on the tensor-core engine (else the SIMT SGEMM)."""
+    return m % 64 == 0 and k % 64 == 0 and n % 64 == 0 and m <= 128 and k * n >= (1 << 22)
+
+
 def colsum(x):
     m, n = x.shape
     out = torch.empty(n, dtype=torch.float32, device=x.device)

@@ -107,6 +107,13 @@ int cmu_sgemm(const float* a, long long sam, long long sak, const float* b, long
               long long ldc, const float* bias, int m, int n, int k, int accumulate, float* workspace,
               long long workspace_bytes, void* stream);
 int cmu_colsum(const float* x, int m, int n, float* out, int accumulate, void* stream);
+/* tensor-core path for the big projector linears: out (qc,pc) fp32 = Q^T P (+ bias[pc]) over the rows of
+ * Q (rows,qc) bf16 and P (rows,pc) bf16 -- the tcgen05 wgrad engine with the matrix rows as the reduction dim */
+long long cmu_gemm_tn_workspace_bytes(int qc, int pc, long long rows);
+int cmu_gemm_tn_bf16(const void* q, int qc, const void* p, int pc, long long rows, float* out, const float* bias,
+                     int accumulate, float* workspace, long long workspace_bytes, void* stream);
+/* fp32 (rows, cols) -> bf16 transposed (cols, rows) [+ optional untransposed bf16 copy y] */
+int cmu_transpose_cast_bf16(const float* x, void* yt, void* y, long long rows, long long cols, void* stream);
 int cmu_bn1d_stats(const float* x, int m, int c, float* stats /* [2][C] */, void* stream);
 int cmu_bn1d_apply(const float* x, const float* stats, double count, int m, int c, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, float momentum, float eps, int training, int relu, float* y,

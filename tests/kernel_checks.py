@@ -348,6 +348,34 @@ def check_mask(seed=60, b=6, s=128, ps=16, ratio=0.65, steps=2):
     return res
 
 
+def check_mask_pair_mode(seed=60, b=5, s=96, steps=4):
+    """CM_UNet's prefetching stream (next step's online+target pair generated on a side stream) serves exactly the
+    masks of the sequential reference order, survives a batch-size change, and reports the logical stream position."""
+    import contrastive_masked_unet_b200 as C
+    from oracle.mask_oracle import MT19937, patch_mask
+    ms = C.MaskStream()
+    ms.pair_mode = True
+    ms.seed(seed, DEV)
+    rng = MT19937(seed)
+    dev = torch.device(DEV)
+    bad = 0
+    batches = [b, b, b, b + 2, b + 2, b]
+    for bb in batches[:steps + 2]:
+        m_on, k = ms.generate(bb, s, 16, 0.65, dev)
+        m_tg, k0 = ms.generate(bb, s, 16, 0.0, dev)
+        ref, _ = patch_mask(rng, bb, s, 16, 0.65)
+        patch_mask(rng, bb, s, 16, 0.0)
+        torch.cuda.synchronize()
+        bad += int((m_on.cpu().numpy() != ref).sum()) + int(m_tg.sum())
+    st = ms.get_numpy_state()
+    r2 = MT19937()
+    r2.set_state(st[1], st[2])
+    ok = [r2.next_u32() for _ in range(3)] == [rng.next_u32() for _ in range(3)]
+    res = {'mismatch_bytes': bad, 'logical_stream_ok': ok, 'prefetch_outstanding': ms._pref is not None}
+    assert bad == 0 and ok, res
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ linear / BN1d / optim
 def check_linear(m=8, k=4096 * 3, n=192, seed=9):
     g = _gen(seed)
@@ -365,6 +393,43 @@ def check_linear(m=8, k=4096 * 3, n=192, seed=9):
     res = {'fwd': rel_err(y, (x.double() @ w.double().t() + b.double())), 'dx': rel_err(dx, dy.double() @ w.double()),
            'dw': rel_err(dw, dy.double().t() @ x.double()), 'db': rel_err(db, dy.sum(0))}
     torch.backends.cuda.matmul.allow_tf32 = prev
+    assert max(res.values()) < 1e-4, res
+    return res
+
+
+def check_gemm_tn(rows=1000, qc=64, pc=256, seed=19, bias=True):
+    g = _gen(seed)
+    q = _randn((rows, qc), g)
+    p = _randn((rows, pc), g)
+    b = _randn((pc,), g) if bias else None
+    qt16, q16 = ops.transpose_cast(q.t().contiguous(), also_plain=True)    # qt16: (rows,qc) from a (qc,rows) source
+    p16 = ops.cast_bf16(p)
+    out = ops.gemm_tn(qt16, p16, bias=b)
+    ref = qt16.double().t() @ p16.double() + (b.double() if bias else 0)
+    torch.cuda.synchronize()
+    res = {'gemm': rel_err(out, ref), 'tcast': float((qt16.float() - q.t().to(BF16).float()).abs().max()),
+           'cast': float((q16.float() - q.t().to(BF16).float()).abs().max())}
+    assert res['gemm'] < 1e-4 and res['tcast'] == 0.0 and res['cast'] == 0.0, res
+    return res
+
+
+def check_linear_tc(m=64, k=4096, n=1536, seed=20):
+    """LinearFn on the tensor-core path vs fp32 autograd on the bf16-rounded operands."""
+    from contrastive_masked_unet_b200 import functional as Fn
+    g = _gen(seed)
+    x = _randn((m, k), g).to(BF16).float().requires_grad_(True)
+    w = _randn((n, k), g, k ** -0.5).to(BF16).float().requires_grad_(True)
+    b = _randn((n,), g).requires_grad_(True)
+    dy = _randn((m, n), g).to(BF16).float()
+    assert ops.tc_linear_ok(m, k, n)
+    y = Fn.LinearFn.apply(x, w, b)
+    y.backward(dy)
+    gx, gw, gb = x.grad.clone(), w.grad.clone(), b.grad.clone()
+    x.grad = w.grad = b.grad = None
+    yr = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    yr.backward(dy.double())
+    torch.cuda.synchronize()
+    res = {'y': rel_err(y, yr.detach()), 'dx': rel_err(gx, x.grad), 'dw': rel_err(gw, w.grad), 'db': rel_err(gb, b.grad)}
     assert max(res.values()) < 1e-4, res
     return res
 
@@ -470,8 +535,14 @@ CHECKS = {
     'mask_512_b64': lambda: check_mask(60, 64, 512, 16, 0.65, 2),
     'mask_224': lambda: check_mask(61, 4, 224, 16, 0.65, 2),
     'mask_ps8': lambda: check_mask(3, 2, 128, 8, 0.5, 1),
+    'mask_pair_mode_prefetch': check_mask_pair_mode,
     'linear': check_linear,
     'linear_small': lambda: check_linear(64, 256, 1536, seed=18),
+    'gemm_tn': check_gemm_tn,
+    'gemm_tn_big_n': lambda: check_gemm_tn(64, 1536, 4096 + 64, seed=21, bias=False),
+    'gemm_tn_splitk': lambda: check_gemm_tn(50000, 64, 128, seed=22),
+    'linear_tc': check_linear_tc,
+    'linear_tc_128rows': lambda: check_linear_tc(128, 8192, 512, seed=23),
     'bn1d': check_bn1d,
     'optim': check_optim,
 }
