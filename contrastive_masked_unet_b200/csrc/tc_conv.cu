@@ -22,8 +22,10 @@ namespace cmu {
 enum { MODE_CONV3 = 0, MODE_PLAIN = 1, MODE_CONVT_FPROP = 2, MODE_CONVT_DGRAD = 3 };
 
 constexpr int kK1Threads = 192;
-constexpr int kAStageBytes = 20480;  // max haloed patch: (8+2) x 16 or (16+2) x 8 rows of 128 B
-constexpr int kStagingBytes = 16384; // one 128 x 64 bf16 output slab
+constexpr int kStagingBytes = 16384;  // one 128 x 64 bf16 output slab
+constexpr int kMaxStages = 8;
+constexpr int kSchedDepth = 4;
+constexpr int kSmemLimit = 232448;    // 227 KB per CTA
 
 struct K1Params {
   CUtensorMap tmA0, tmA1, tmB, tmO0, tmO1;
@@ -35,18 +37,12 @@ struct K1Params {
   int TW, TH, tw_shift;
   int tiles_w, tiles_h, m_tiles, n_tiles;
   int kc;           // number of 64-wide K chunks per tap
+  // shared-memory plan (host-computed): [n_stages x stage_bytes][stg_bufs x 16 KB staging][barriers][stats]
+  int a_bytes, b_bytes, b_off, stage_bytes, n_stages, stg_bufs;
+  unsigned int* sched;  // [n_tiles] m-tile counters, zeroed before the launch (dynamic tile scheduler)
   const float* bias;
   int bias_mod;
   float* stats;     // [gridDim.x][2][BN] partial (sum, sum of squares) or nullptr
-};
-
-template <int BN>
-struct K1Cfg {
-  static constexpr int kBStage = 3 * BN * 128;
-  static constexpr int kStage = kAStageBytes + kBStage;
-  static constexpr int kStages = (BN == 128) ? 3 : 4;
-  static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmem = kStages * kStage + kStagingBytes + 1024 /*align*/ + 1024 /*barriers+stats*/ + 2 * BN * 4;
 };
 
 template <int OFF>
@@ -68,32 +64,44 @@ __device__ __forceinline__ void column_sums(float (&v)[32], uint32_t lane) {
   bfly<1>(v, lane);
 }
 
+// Tile scheduling: every CTA owns ONE n-tile (blockIdx % n_tiles; its BatchNorm partial sums live in one smem slot)
+// and pulls m-tiles of that n-tile from a global atomic counter.  The producer thread fetches tile indices and
+// publishes them to the MMA and epilogue warps through a small smem ring, so a CTA that starts late (another
+// kernel holding its SM) or runs slow simply takes fewer tiles -- no static tail.
 template <int BN>
 __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant__ K1Params p) {
-  using Cfg = K1Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  uint8_t* staging = smem + Cfg::kStages * Cfg::kStage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
-  uint64_t* full_bar = bars;                      // [kStages]
-  uint64_t* empty_bar = bars + Cfg::kStages;      // [kStages]
-  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;  // [2]
-  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* s_stats = reinterpret_cast<float*>(bars + 32);  // [2][BN]
+  uint8_t* staging = smem + p.n_stages * p.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + p.stg_bufs * kStagingBytes);
+  uint64_t* full_bar = bars;                          // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;               // [2]
+  uint64_t* sfull_bar = tempty_bar + 2;               // [kSchedDepth]
+  uint64_t* sempty_bar = sfull_bar + kSchedDepth;     // [kSchedDepth]
+  int* sched_tile = reinterpret_cast<int*>(sempty_bar + kSchedDepth);  // [kSchedDepth]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_tile + kSchedDepth);
+  float* s_stats = reinterpret_cast<float*>(bars + 40);  // [2][BN]
+  constexpr uint32_t kTmemCols = 2 * BN;
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
+  const int n_stages = p.n_stages;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < Cfg::kStages; ++i) {
+    for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
+    }
+    for (int i = 0; i < kSchedDepth; ++i) {
+      mbar_init(&sfull_bar[i], 1);
+      mbar_init(&sempty_bar[i], 5);  // MMA lane + one lane of each of the 4 epilogue warps
     }
     fence_mbar_init();
     tma_prefetch_desc(&p.tmA0);
@@ -102,7 +110,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
   }
   for (int i = threadIdx.x; i < 2 * BN; i += kK1Threads) s_stats[i] = 0.f;
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -110,34 +118,38 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile schedule: this CTA owns one n-tile (so its BN statistics stay in one smem slot) and strides over m-tiles
   const int nt = blockIdx.x % p.n_tiles;
-  const int mt0 = blockIdx.x / p.n_tiles;
-  const int mstride = gridDim.x / p.n_tiles;
   const int n0 = nt * BN;
   const int shifts = (p.mode == MODE_CONV3) ? 3 : 1;
   const int kc = p.kc;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ scheduler + TMA producer
     if (lane == 0) {
-      const uint32_t a_bytes = (p.mode == MODE_CONV3) ? (p.TH + 2) * p.TW * 128 : 128 * 128;
-      const uint32_t b_total = (p.mode == MODE_CONV3) ? 3 * BN * 128 : BN * 128;
-      uint32_t it = 0;
-      for (int mt = mt0; mt < p.m_tiles; mt += mstride) {
+      const uint32_t tx_bytes = p.a_bytes + p.b_bytes;
+      uint32_t it = 0, sit = 0;
+      while (true) {
+        const uint32_t sslot = sit % kSchedDepth;
+        mbar_wait(&sempty_bar[sslot], ((sit / kSchedDepth) & 1) ^ 1);
+        const int t = (int)atomicAdd(p.sched + nt, 1u);
+        const int mt = (t < p.m_tiles) ? t : -1;
+        sched_tile[sslot] = mt;
+        mbar_arrive(&sfull_bar[sslot]);
+        ++sit;
+        if (mt < 0) break;
         const int img = mt / tiles_per_img;
         const int rem = mt - img * tiles_per_img;
         const int h0 = (rem / p.tiles_w) * p.TH;
         const int w0 = (rem % p.tiles_w) * p.TW;
         for (int c = 0; c < kc; ++c) {
           for (int s = 0; s < shifts; ++s, ++it) {
-            const uint32_t st = it % Cfg::kStages;
-            const uint32_t ph = (it / Cfg::kStages) & 1;
+            const uint32_t st = it % n_stages;
+            const uint32_t ph = (it / n_stages) & 1;
             mbar_wait(&empty_bar[st], ph ^ 1);
-            uint8_t* sA = stage_base + st * Cfg::kStage;
-            uint8_t* sB = sA + kAStageBytes;
-            mbar_arrive_expect_tx(&full_bar[st], a_bytes + b_total);
+            uint8_t* sA = stage_base + st * p.stage_bytes;
+            uint8_t* sB = sA + p.b_off;
+            mbar_arrive_expect_tx(&full_bar[st], tx_bytes);
             if (p.mode == MODE_CONVT_DGRAD) {
               const int per = p.c0 >> 6;
               const int rs = c / per;
@@ -165,21 +177,28 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
       const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
       const int taps = (p.mode == MODE_CONV3) ? 3 : 1;
       const uint32_t a_tap_stride = p.TW * 128;
-      uint32_t it = 0, tile_it = 0;
-      for (int mt = mt0; mt < p.m_tiles; mt += mstride, ++tile_it) {
+      uint32_t it = 0, tile_it = 0, sit = 0;
+      while (true) {
+        const uint32_t sslot = sit % kSchedDepth;
+        mbar_wait(&sfull_bar[sslot], (sit / kSchedDepth) & 1);
+        const int mt = sched_tile[sslot];
+        mbar_arrive(&sempty_bar[sslot]);
+        ++sit;
+        if (mt < 0) break;
         const uint32_t acc = tile_it & 1;
         const uint32_t aph = (tile_it >> 1) & 1;
+        ++tile_it;
         mbar_wait(&tempty_bar[acc], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         const int nstages = kc * shifts;
         for (int sidx = 0; sidx < nstages; ++sidx, ++it) {
-          const uint32_t st = it % Cfg::kStages;
-          const uint32_t ph = (it / Cfg::kStages) & 1;
+          const uint32_t st = it % n_stages;
+          const uint32_t ph = (it / n_stages) & 1;
           mbar_wait(&full_bar[st], ph);
           tc_fence_after();
-          const uint32_t sA = smem_u32(stage_base + st * Cfg::kStage);
-          const uint32_t sB = sA + kAStageBytes;
+          const uint32_t sA = smem_u32(stage_base + st * p.stage_bytes);
+          const uint32_t sB = sA + p.b_off;
           for (int r = 0; r < taps; ++r) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -201,8 +220,16 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
     const bool store_thread = (threadIdx.x == 64);
     const int th = row >> p.tw_shift;
     const int tw = row & (p.TW - 1);
-    uint32_t tile_it = 0;
-    for (int mt = mt0; mt < p.m_tiles; mt += mstride, ++tile_it) {
+    const int stg_bufs = p.stg_bufs;
+    uint32_t tile_it = 0, sit = 0, slab_it = 0;
+    while (true) {
+      const uint32_t sslot = sit % kSchedDepth;
+      mbar_wait(&sfull_bar[sslot], (sit / kSchedDepth) & 1);
+      const int mt = sched_tile[sslot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sempty_bar[sslot]);
+      ++sit;
+      if (mt < 0) break;
       const int img = mt / tiles_per_img;
       const int rem = mt - img * tiles_per_img;
       const int h0 = (rem / p.tiles_w) * p.TH;
@@ -210,11 +237,16 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
       const bool valid = (h0 + th < p.H) && (w0 + tw < p.W);
       const uint32_t acc = tile_it & 1;
       const uint32_t aph = (tile_it >> 1) & 1;
+      ++tile_it;
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int slab = 0; slab < BN / 64; ++slab) {
-        if (store_thread) tma_store_wait_read0();  // previous store has finished reading the staging buffer
+      for (int slab = 0; slab < BN / 64; ++slab, ++slab_it) {
+        uint8_t* stg = staging + (slab_it % stg_bufs) * kStagingBytes;
+        if (store_thread) {  // the store that last used this staging buffer has finished reading it
+          if (stg_bufs == 2) tma_store_wait_read1();
+          else tma_store_wait_read0();
+        }
         named_bar_sync(1, 128);
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -236,7 +268,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
             for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + cb + i);
           }
           // bf16 pack + swizzled staging store (16-byte chunk index XOR (row & 7): TMA SWIZZLE_128B pattern)
-          uint8_t* rowp = staging + row * 128;
+          uint8_t* rowp = stg + row * 128;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             uint4 pk;
@@ -268,11 +300,11 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
           if (p.mode == MODE_CONVT_FPROP) {
             const int rs = nch / p.oc0;
             const int co = nch - rs * p.oc0;
-            tma_store_5d(&p.tmO0, staging, (rs & 1) * p.oc0 + co, w0, rs >> 1, h0, img);
+            tma_store_5d(&p.tmO0, stg, (rs & 1) * p.oc0 + co, w0, rs >> 1, h0, img);
           } else if (nch < p.oc0) {
-            tma_store_4d(&p.tmO0, staging, nch, w0, h0, img);
+            tma_store_4d(&p.tmO0, stg, nch, w0, h0, img);
           } else {
-            tma_store_4d(&p.tmO1, staging, nch - p.oc0, w0, h0, img);
+            tma_store_4d(&p.tmO1, stg, nch - p.oc0, w0, h0, img);
           }
           tma_store_commit();
         }
@@ -288,9 +320,15 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
+
+// Global m-tile counters of the dynamic scheduler: a ring of slots, one per launch, zeroed (stream-ordered) before
+// the launch that uses it.  Static device memory -- the library still never allocates.
+constexpr int kSchedSlots = 512;
+constexpr int kSchedWidth = 32;
+__device__ unsigned int g_sched_counters[kSchedSlots * kSchedWidth];
 
 // ---------------------------------------------------------------------------------------------- host side
 static bool pick_tile(int mode, int H, int W, int* TW, int* TH) {
@@ -338,14 +376,25 @@ static int make_w_map(CUtensorMap* m, const void* base, int taps, int n_rows, in
 }
 
 template <int BN>
-static int launch_k1(const K1Params& p, int grid, cudaStream_t stream) {
+static int launch_k1(const K1Params& p, int grid, int smem_bytes, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    CMU_CHECK_CUDA(cudaFuncSetAttribute(k1_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1Cfg<BN>::kSmem));
+    CMU_CHECK_CUDA(cudaFuncSetAttribute(k1_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
-  k1_kernel<BN><<<grid, kK1Threads, K1Cfg<BN>::kSmem, stream>>>(p);
+  k1_kernel<BN><<<grid, kK1Threads, smem_bytes, stream>>>(p);
   CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+static int next_sched_slot(unsigned int** out, int n_tiles, cudaStream_t stream) {
+  static unsigned int* base = nullptr;
+  static unsigned int counter = 0;
+  if (base == nullptr) CMU_CHECK_CUDA(cudaGetSymbolAddress((void**)&base, g_sched_counters));
+  CMU_REQUIRE(n_tiles <= kSchedWidth, "k1: too many n-tiles (%d)", n_tiles);
+  unsigned int* slot = base + (size_t)(counter++ % kSchedSlots) * kSchedWidth;
+  CMU_CHECK_CUDA(cudaMemsetAsync(slot, 0, kSchedWidth * sizeof(unsigned int), stream));
+  *out = slot;
   return 0;
 }
 
@@ -415,13 +464,25 @@ static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int 
       p.tmO1 = p.tmO0;
     }
   }
+  // shared-memory plan
+  p.a_bytes = (mode == MODE_CONV3) ? (p.TH + 2) * p.TW * 128 : 128 * 128;
+  p.b_bytes = ((mode == MODE_CONV3) ? 3 : 1) * BN * 128;
+  p.b_off = (p.a_bytes + 1023) & ~1023;
+  p.stage_bytes = p.b_off + p.b_bytes;
+  const int fixed = 1024 /*align*/ + 320 /*barriers*/ + 2 * BN * 4 + 64;
+  p.stg_bufs = ((kSmemLimit - fixed - 2 * kStagingBytes) / p.stage_bytes >= 4) ? 2 : 1;
+  p.n_stages = (kSmemLimit - fixed - p.stg_bufs * kStagingBytes) / p.stage_bytes;
+  if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
+  CMU_REQUIRE(p.n_stages >= 2, "k1: shared-memory plan failed (stage %d bytes)", p.stage_bytes);
+  const int smem_bytes = p.n_stages * p.stage_bytes + p.stg_bufs * kStagingBytes + fixed;
+  if (next_sched_slot(&p.sched, p.n_tiles, stream)) return 1;
   int grid = num_sms();
   const int total_tiles = p.m_tiles * p.n_tiles;
   if (grid > total_tiles) grid = total_tiles;
   grid = (grid / p.n_tiles) * p.n_tiles;
   if (grid < p.n_tiles) grid = p.n_tiles;
   if (stats_grid) *stats_grid = grid;
-  return BN == 128 ? launch_k1<128>(p, grid, stream) : launch_k1<64>(p, grid, stream);
+  return BN == 128 ? launch_k1<128>(p, grid, smem_bytes, stream) : launch_k1<64>(p, grid, smem_bytes, stream);
 }
 
 }  // namespace cmu
