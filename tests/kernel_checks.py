@@ -407,7 +407,7 @@ def check_gemm_tn(rows=1000, qc=64, pc=256, seed=19, bias=True):
     out = ops.gemm_tn(qt16, p16, bias=b)
     ref = qt16.double().t() @ p16.double() + (b.double() if bias else 0)
     torch.cuda.synchronize()
-    res = {'gemm': rel_err(out, ref), 'tcast': float((qt16.float() - q.t().to(BF16).float()).abs().max()),
+    res = {'gemm': rel_err(out, ref), 'tcast': float((qt16.float() - q.to(BF16).float()).abs().max()),
            'cast': float((q16.float() - q.t().to(BF16).float()).abs().max())}
     assert res['gemm'] < 1e-4 and res['tcast'] == 0.0 and res['cast'] == 0.0, res
     return res
