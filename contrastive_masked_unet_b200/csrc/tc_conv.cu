@@ -129,15 +129,22 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
     if (lane == 0) {
       const uint32_t tx_bytes = p.a_bytes + p.b_bytes;
       uint32_t it = 0, sit = 0;
+      // dynamic: m-tiles come from a global counter, fetched ONE TILE AHEAD so that the atomic's round trip overlaps
+      // the loads of the current tile; static (sched == nullptr, A/B switch): blockIdx-strided like a classic
+      // persistent kernel.
+      const int mstride = gridDim.x / p.n_tiles;
+      int static_next = blockIdx.x / p.n_tiles;
+      int t_next = p.sched ? (int)atomicAdd(p.sched + nt, 1u) : static_next;
       while (true) {
         const uint32_t sslot = sit % kSchedDepth;
         mbar_wait(&sempty_bar[sslot], ((sit / kSchedDepth) & 1) ^ 1);
-        const int t = (int)atomicAdd(p.sched + nt, 1u);
-        const int mt = (t < p.m_tiles) ? t : -1;
+        const int mt = (t_next < p.m_tiles) ? t_next : -1;
         sched_tile[sslot] = mt;
         mbar_arrive(&sfull_bar[sslot]);
         ++sit;
         if (mt < 0) break;
+        if (p.sched) t_next = (int)atomicAdd(p.sched + nt, 1u);
+        else t_next = (static_next += mstride);
         const int img = mt / tiles_per_img;
         const int rem = mt - img * tiles_per_img;
         const int h0 = (rem / p.tiles_w) * p.TH;
@@ -475,7 +482,8 @@ static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int 
   if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
   CMU_REQUIRE(p.n_stages >= 2, "k1: shared-memory plan failed (stage %d bytes)", p.stage_bytes);
   const int smem_bytes = p.n_stages * p.stage_bytes + p.stg_bufs * kStagingBytes + fixed;
-  if (next_sched_slot(&p.sched, p.n_tiles, stream)) return 1;
+  if (debug_knob(3) == 1) p.sched = nullptr;   // A/B switch: static tile schedule
+  else if (next_sched_slot(&p.sched, p.n_tiles, stream)) return 1;
   int grid = num_sms();
   const int total_tiles = p.m_tiles * p.n_tiles;
   if (grid > total_tiles) grid = total_tiles;

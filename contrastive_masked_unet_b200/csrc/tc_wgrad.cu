@@ -258,22 +258,21 @@ static void plan_k2(int mode, int N, int H, int W, int qc, int pc, K2Plan* pl) {
   pl->NT = pc / pl->n_cols;
   pl->G = (mode == 0) ? 3 : (mode == 1 ? 4 : 1);
   pl->taps = (mode == 0) ? 3 : 1;
-  // split-K over pixel tiles: pick the split count whose CTA count fills whole waves of the machine (a 192-CTA
-  // grid on 148 SMs would run two waves at 65 % efficiency) and prefer >= 2 waves of shorter CTAs, which also keeps
-  // the kernel insensitive to an SM being held by a concurrent kernel (the side-stream mask generator).
+  // split-K over pixel tiles.  Cost model: a launch takes waves(s) x (pixel tiles per CTA + fixed CTA cost), the fixed
+  // cost (TMEM alloc, pipeline fill, fp32 partial-block epilogue) being worth ~10 pixel-tile stages.  This fills the
+  // machine for small layers and repairs the 1.3-wave quantisation of the big ones (192 CTAs on 148 SMs).
   const int base = pl->MT * pl->NT * pl->G;
   const int sms = num_sms();
   const long long per_split_bytes = (long long)pl->G * pl->taps * qc * pc * 4;
   int splits = 1;
-  double best = -1.0;
+  double best = 1e300;
   for (int sp = 1; sp <= pl->pix_tiles && sp <= 1024; ++sp) {
     const long long ctas = (long long)base * sp;
-    if (sp > 1 && (ctas > 6ll * sms || per_split_bytes * sp > (768ll << 20))) break;
+    if (sp > 1 && (ctas > 4ll * sms || per_split_bytes * sp > (768ll << 20))) break;
     const long long waves = (ctas + sms - 1) / sms;
-    const double eff = (double)ctas / (double)(waves * sms);
-    const double score = eff + (waves >= 2 ? 0.05 : 0.0) - 0.004 * (double)waves;
-    if (score > best) {
-      best = score;
+    const double cost = (double)waves * ((double)pl->pix_tiles / sp + 10.0);
+    if (cost < best * 0.999) {
+      best = cost;
       splits = sp;
     }
   }

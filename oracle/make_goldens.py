@@ -180,7 +180,7 @@ def main():
         json.dump({'meta': meta, 'case': gold_finetune()}, open(os.path.join(GOLD, 'finetune.json'), 'w'), indent=1)
         print('finetune done')
     if 'pretrain' in which:
-        cases = [gold_pretrain(64, 8), gold_pretrain(224, 4), gold_pretrain(512, 2)]
+        cases = [gold_pretrain(64, 8), gold_pretrain(224, 4), gold_pretrain(512, 2), gold_pretrain(224, 8)]
         json.dump({'meta': meta, 'cases': cases}, open(os.path.join(GOLD, 'pretrain.json'), 'w'), indent=1)
         print('pretrain done', [c['seconds'] for c in cases])
 

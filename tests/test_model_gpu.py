@@ -17,10 +17,12 @@ def test_pretrain_step_S64_B8_vs_oracle_and_golden():
     assert not rep['fails'], (rep['fails'][:8], {k: v for k, v in rep.items() if k not in ('fails', 'cos_table')})
 
 
-def test_pretrain_step_S224_B4_reference_native_size():
+def test_pretrain_step_S224_B8_reference_native_size():
+    """224 x 224 is the size the unmodified reference runs at (cmunet.py:130 literal).  B = 8: with fewer rows the
+    SyncBN of the projection head (statistics over B rows) makes loss_ct ill-conditioned in ANY reduced precision."""
     _gpu()
     from tests import model_checks as M
-    rep = M.pretrain_parity(224, 4, golden=M.golden_pretrain(224, 4))
+    rep = M.pretrain_parity(224, 8, golden=M.golden_pretrain(224, 8))
     assert not rep['fails'], (rep['fails'][:8], {k: v for k, v in rep.items() if k not in ('fails', 'cos_table')})
 
 

@@ -64,6 +64,11 @@ def test_pretrain_S512():
     run_pretrain_case(PRE[2])
 
 
+@pytest.mark.slow
+def test_pretrain_S224_B8():
+    run_pretrain_case(PRE[3])
+
+
 def test_finetune_config1():
     c = FT
     torch.manual_seed(c['seed'])
