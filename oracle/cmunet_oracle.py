@@ -122,7 +122,10 @@ class OracleDecoder(nn.Module):
 
 class OracleNeck(nn.Module):
     """CMU/necks/nonlinear_neck.py:35-103 with the config of configs/cmunet_config.py:18-38:
-    x[:,0,:] -> flatten -> fc0(+bias) -> (Sync)BN(eps 1e-6) -> ReLU -> fc1(no bias)."""
+    x[:,0,:] -> flatten -> fc0(+bias) -> (Sync)BN(eps 1e-6) -> ReLU -> fc1(no bias).
+    sync_bn: nn.SyncBatchNorm semantics across ranks (what the reference runs on GPUs); False reproduces the CPU shim
+    of oracle/ref_loader.py (unsynced BatchNorm1d), which is what the 2-rank CPU golden was minted with."""
+    sync_bn = True
 
     def __init__(self, in_channels, hid_channels=1536, out_channels=256):
         super().__init__()
@@ -134,7 +137,7 @@ class OracleNeck(nn.Module):
         x = x[:, 0, :].reshape(x.size(0), -1)
         x = F.linear(x, self.fc0.weight, self.fc0.bias)
         bn = self.bn0
-        if bn.training and torch.distributed.is_available() and torch.distributed.is_initialized() \
+        if self.sync_bn and bn.training and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
             x = _sync_bn_train(bn, x)
         else:
