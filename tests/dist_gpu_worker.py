@@ -22,7 +22,7 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = False
     import contrastive_masked_unet_b200 as C
     from oracle import cmunet_oracle as O
-    S, B, seed = 64, 8, 60
+    S, B, seed = 64, 16, 60
     torch.manual_seed(seed)
     np.random.seed(seed + rank)
     m = C.build(C.cmunet_config(S))
