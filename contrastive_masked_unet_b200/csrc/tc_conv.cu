@@ -39,6 +39,8 @@ struct K1Params {
   int kc;           // number of 64-wide K chunks per tap
   // shared-memory plan (host-computed): [n_stages x stage_bytes][stg_bufs x 16 KB staging][barriers][stats]
   int a_bytes, b_bytes, b_off, stage_bytes, n_stages, stg_bufs;
+  int w_resident;   // 1: this CTA's whole weight slab (all taps x K chunks of its n-tile) is loaded ONCE into shared
+  int w_bytes;      //    memory and the pipeline streams activations only (small-weight layers)
   unsigned int* sched;  // [n_tiles] m-tile counters, zeroed before the launch (dynamic tile scheduler)
   const float* bias;
   int bias_mod;
@@ -72,8 +74,9 @@ template <int BN>
 __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant__ K1Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_base = smem;
-  uint8_t* staging = smem + p.n_stages * p.stage_bytes;
+  uint8_t* w_res = smem;                                   // [w_bytes] resident weights (w_resident mode)
+  uint8_t* stage_base = smem + p.w_bytes;
+  uint8_t* staging = stage_base + p.n_stages * p.stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + p.stg_bufs * kStagingBytes);
   uint64_t* full_bar = bars;                          // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]
@@ -81,7 +84,8 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
   uint64_t* tempty_bar = tfull_bar + 2;               // [2]
   uint64_t* sfull_bar = tempty_bar + 2;               // [kSchedDepth]
   uint64_t* sempty_bar = sfull_bar + kSchedDepth;     // [kSchedDepth]
-  int* sched_tile = reinterpret_cast<int*>(sempty_bar + kSchedDepth);  // [kSchedDepth]
+  uint64_t* wfull_bar = sempty_bar + kSchedDepth;     // [1]
+  int* sched_tile = reinterpret_cast<int*>(wfull_bar + 1);  // [kSchedDepth]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_tile + kSchedDepth);
   float* s_stats = reinterpret_cast<float*>(bars + 40);  // [2][BN]
   constexpr uint32_t kTmemCols = 2 * BN;
@@ -103,6 +107,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
       mbar_init(&sfull_bar[i], 1);
       mbar_init(&sempty_bar[i], 5);  // MMA lane + one lane of each of the 4 epilogue warps
     }
+    mbar_init(wfull_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.tmA0);
     tma_prefetch_desc(&p.tmB);
@@ -127,7 +132,14 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------------ scheduler + TMA producer
     if (lane == 0) {
-      const uint32_t tx_bytes = p.a_bytes + p.b_bytes;
+      const uint32_t tx_bytes = p.a_bytes + (p.w_resident ? 0 : p.b_bytes);
+      if (p.w_resident) {   // one-time load of this n-tile's weights: kc x shifts boxes
+        mbar_arrive_expect_tx(wfull_bar, p.w_bytes);
+        for (int c = 0; c < kc; ++c)
+          for (int s = 0; s < shifts; ++s)
+            tma_load_3d(w_res + (c * shifts + s) * p.b_bytes, &p.tmB, wfull_bar, c << 6, n0,
+                        (p.mode == MODE_CONV3) ? 3 * s : 0);
+      }
       uint32_t it = 0, sit = 0;
       // dynamic: m-tiles come from a global counter, fetched ONE TILE AHEAD so that the atomic's round trip overlaps
       // the loads of the current tile; static (sched == nullptr, A/B switch): blockIdx-strided like a classic
@@ -172,7 +184,8 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
               else
                 tma_load_4d(sA, src, &full_bar[st], cc, w0, h0, img);
             }
-            tma_load_3d(sB, &p.tmB, &full_bar[st], c << 6, n0, (p.mode == MODE_CONV3) ? 3 * s : 0);
+            if (!p.w_resident)
+              tma_load_3d(sB, &p.tmB, &full_bar[st], c << 6, n0, (p.mode == MODE_CONV3) ? 3 * s : 0);
           }
         }
       }
@@ -185,6 +198,8 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
       const int taps = (p.mode == MODE_CONV3) ? 3 : 1;
       const uint32_t a_tap_stride = p.TW * 128;
       uint32_t it = 0, tile_it = 0, sit = 0;
+      const uint32_t w_base = smem_u32(w_res);
+      if (p.w_resident) mbar_wait(wfull_bar, 0);
       while (true) {
         const uint32_t sslot = sit % kSchedDepth;
         mbar_wait(&sfull_bar[sslot], (sit / kSchedDepth) & 1);
@@ -205,7 +220,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
           mbar_wait(&full_bar[st], ph);
           tc_fence_after();
           const uint32_t sA = smem_u32(stage_base + st * p.stage_bytes);
-          const uint32_t sB = sA + p.b_off;
+          const uint32_t sB = p.w_resident ? w_base + sidx * p.b_bytes : sA + p.b_off;   // sidx = c * shifts + s
           for (int r = 0; r < taps; ++r) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -477,11 +492,21 @@ static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int 
   p.b_off = (p.a_bytes + 1023) & ~1023;
   p.stage_bytes = p.b_off + p.b_bytes;
   const int fixed = 1024 /*align*/ + 320 /*barriers*/ + 2 * BN * 4 + 64;
-  p.stg_bufs = ((kSmemLimit - fixed - 2 * kStagingBytes) / p.stage_bytes >= 4) ? 2 : 1;
-  p.n_stages = (kSmemLimit - fixed - p.stg_bufs * kStagingBytes) / p.stage_bytes;
+  // small-weight layers: keep the n-tile's whole weight slab resident, stream activations only
+  const int w_all = p.kc * p.b_bytes;
+  p.w_resident = 0;
+  p.w_bytes = 0;
+  if (debug_knob(4) != 1 && mode != MODE_CONVT_DGRAD && p.m_tiles >= 4 * num_sms() &&
+      (kSmemLimit - fixed - kStagingBytes - w_all) / p.b_off >= 3) {
+    p.w_resident = 1;
+    p.w_bytes = w_all;
+    p.stage_bytes = p.b_off;
+  }
+  p.stg_bufs = ((kSmemLimit - fixed - p.w_bytes - 2 * kStagingBytes) / p.stage_bytes >= 4) ? 2 : 1;
+  p.n_stages = (kSmemLimit - fixed - p.w_bytes - p.stg_bufs * kStagingBytes) / p.stage_bytes;
   if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
   CMU_REQUIRE(p.n_stages >= 2, "k1: shared-memory plan failed (stage %d bytes)", p.stage_bytes);
-  const int smem_bytes = p.n_stages * p.stage_bytes + p.stg_bufs * kStagingBytes + fixed;
+  const int smem_bytes = p.w_bytes + p.n_stages * p.stage_bytes + p.stg_bufs * kStagingBytes + fixed;
   if (debug_knob(3) == 1) p.sched = nullptr;   // A/B switch: static tile schedule
   else if (next_sched_slot(&p.sched, p.n_tiles, stream)) return 1;
   int grid = num_sms();
