@@ -493,7 +493,7 @@ static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int 
   p.stage_bytes = p.b_off + p.b_bytes;
   const int fixed = 1024 /*align*/ + 320 /*barriers*/ + 2 * BN * 4 + 64;
   // small-weight layers: keep the n-tile's whole weight slab resident, stream activations only
-  const int w_all = p.kc * p.b_bytes;
+  const int w_all = p.kc * ((mode == MODE_CONV3) ? 3 : 1) * p.b_bytes;   // all taps x K chunks of one n-tile
   p.w_resident = 0;
   p.w_bytes = 0;
   if (debug_knob(4) != 1 && mode != MODE_CONVT_DGRAD && p.m_tiles >= 4 * num_sms() &&

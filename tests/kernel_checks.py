@@ -515,6 +515,10 @@ CHECKS = {
     'conv3x3_512_1024_tiny': lambda: check_conv3x3(2, 4, 4, 512, 0, 1024, seed=4),
     'conv3x3_cat_512+512_512': lambda: check_conv3x3(1, 8, 8, 512, 512, 512, seed=5),
     'conv3x3_64_128_big': lambda: check_conv3x3(4, 128, 128, 64, 0, 128, seed=6),
+    'conv3x3_64_64_resident_weights': lambda: check_conv3x3(6, 128, 128, 64, 0, 64, seed=7),
+    'conv3x3_cat_64+64_64_resident': lambda: check_conv3x3(6, 128, 128, 64, 64, 64, seed=8),
+    'conv3x3_64_128_resident': lambda: check_conv3x3(6, 128, 128, 64, 0, 128, seed=9),
+    'convT_128_64_resident': lambda: check_convT(8, 64, 128, 128, 64, seed=14),
     'conv3x3_fprop_only_64_64': lambda: check_conv3x3_fprop_only(2, 24, 40, 64, 0, 64),
     'conv3x3_wgrad_only_64_64': lambda: check_conv3x3_wgrad_only(2, 24, 40, 64, 0, 64),
     'conv3x3_wgrad_only_128_128': lambda: check_conv3x3_wgrad_only(2, 16, 16, 128, 0, 128, seed=1),
