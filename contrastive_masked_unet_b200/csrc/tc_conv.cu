@@ -193,48 +193,66 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-      const int taps = (p.mode == MODE_CONV3) ? 3 : 1;
-      const uint32_t a_tap_stride = p.TW * 128;
-      uint32_t it = 0, tile_it = 0, sit = 0;
-      const uint32_t w_base = smem_u32(w_res);
-      if (p.w_resident) mbar_wait(wfull_bar, 0);
-      while (true) {
-        const uint32_t sslot = sit % kSchedDepth;
-        mbar_wait(&sfull_bar[sslot], (sit / kSchedDepth) & 1);
-        const int mt = sched_tile[sslot];
-        mbar_arrive(&sempty_bar[sslot]);
-        ++sit;
-        if (mt < 0) break;
-        const uint32_t acc = tile_it & 1;
-        const uint32_t aph = (tile_it >> 1) & 1;
-        ++tile_it;
-        mbar_wait(&tempty_bar[acc], aph ^ 1);
+    // The WHOLE warp runs this loop so that every address / descriptor is warp-uniform (kept in uniform registers);
+    // one elected lane issues the tcgen05 instructions.  (With a single-lane branch around the loop the compiler had
+    // to broadcast each descriptor through R2UR + an ELECT loop: ~22 instructions per MMA, which made the kernel
+    // MMA-issue bound -- profiles/r1_k1_ncu_full.md.)
+    const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+    const uint32_t a_tap_stride = p.TW * 128;
+    const bool conv3 = (p.mode == MODE_CONV3);
+    uint32_t it = 0, tile_it = 0, sit = 0;
+    const uint32_t w_base = smem_u32(w_res);
+    const uint32_t stage0 = smem_u32(stage_base);
+    // descriptor high words are constant: LBO = 16 B (unused for swizzled K-major), SBO = 1024 B, version 1, SW128
+    const uint64_t desc_hi = umma_smem_desc(0, 16, 1024);
+    if (p.w_resident) mbar_wait(wfull_bar, 0);
+    while (true) {
+      const uint32_t sslot = sit % kSchedDepth;
+      mbar_wait(&sfull_bar[sslot], (sit / kSchedDepth) & 1);
+      const int mt = sched_tile[sslot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sempty_bar[sslot]);
+      ++sit;
+      if (mt < 0) break;
+      const uint32_t acc = tile_it & 1;
+      const uint32_t aph = (tile_it >> 1) & 1;
+      ++tile_it;
+      mbar_wait(&tempty_bar[acc], aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      const int nstages = kc * shifts;
+      for (int sidx = 0; sidx < nstages; ++sidx, ++it) {
+        const uint32_t st = it % n_stages;
+        const uint32_t ph = (it / n_stages) & 1;
+        mbar_wait(&full_bar[st], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        const int nstages = kc * shifts;
-        for (int sidx = 0; sidx < nstages; ++sidx, ++it) {
-          const uint32_t st = it % n_stages;
-          const uint32_t ph = (it / n_stages) & 1;
-          mbar_wait(&full_bar[st], ph);
-          tc_fence_after();
-          const uint32_t sA = smem_u32(stage_base + st * p.stage_bytes);
-          const uint32_t sB = p.w_resident ? w_base + sidx * p.b_bytes : sA + p.b_off;   // sidx = c * shifts + s
-          for (int r = 0; r < taps; ++r) {
+        const uint32_t sA = stage0 + st * p.stage_bytes;
+        const uint32_t sB = p.w_resident ? w_base + sidx * p.b_bytes : sA + p.b_off;   // sidx = c * shifts + s
+        const uint64_t a0 = desc_hi | (uint64_t)((sA >> 4) & 0x3FFF);
+        const uint64_t b0 = desc_hi | (uint64_t)((sB >> 4) & 0x3FFF);
+        if (elect_one()) {
+          if (conv3) {
+            const uint32_t ta = a_tap_stride >> 4;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = umma_smem_desc(sA + r * a_tap_stride + k * 32, 16, 1024);
-              const uint64_t bd = umma_smem_desc(sB + r * (BN * 128) + k * 32, 16, 1024);
-              umma_bf16(d_tmem, ad, bd, idesc, (sidx | r | k) != 0 ? 1u : 0u);
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                // start-address field is in 16-byte units: +2 per K16 step (32 B), + tap stride per kernel row
+                umma_bf16(d_tmem, a0 + (uint64_t)(r * ta + k * 2), b0 + (uint64_t)(r * (BN * 8) + k * 2), idesc,
+                          (sidx | r | k) != 0 ? 1u : 0u);
+              }
             }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, a0 + (uint64_t)(k * 2), b0 + (uint64_t)(k * 2), idesc, (sidx | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[st]);  // smem slot reusable once these MMAs have read it
+          if (sidx == nstages - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
         }
-        umma_commit(&tfull_bar[acc]);   // accumulator complete
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const uint32_t q = warp & 3;  // TMEM lane quadrant this warp may access

@@ -114,32 +114,39 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, p.n_cols, 1, 1);
-      const uint32_t a_lbo = (p.m_atoms == 2) ? kQAtom : 0;   // M = 64: both M atoms alias the same 64 channels
-      const uint32_t b_lbo = kPAtom;
-      const uint32_t tap_stride = p.TW * 128;
-      uint32_t it = 0;
-      for (int t = t_begin; t < t_end; ++t, ++it) {
-        const uint32_t st = it % kK2Stages;
-        const uint32_t ph = (it / kK2Stages) & 1;
-        mbar_wait(&full_bar[st], ph);
-        tc_fence_after();
-        const uint32_t sQ = smem_u32(smem + st * kK2Stage);
-        const uint32_t sP = sQ + 2 * kQAtom;
-        for (int r = 0; r < p.taps; ++r) {
+    // whole warp runs the loop (warp-uniform descriptors in uniform registers), one elected lane issues
+    const uint32_t idesc = umma_idesc_bf16(128, p.n_cols, 1, 1);
+    const uint32_t a_lbo = (p.m_atoms == 2) ? kQAtom : 0;   // M = 64: both M atoms alias the same 64 channels
+    // MN-major SWIZZLE_128B: LBO = byte stride between 64-channel atoms, SBO = stride between 8-pixel K groups
+    const uint64_t a_hi = umma_smem_desc(0, a_lbo, 1024);
+    const uint64_t b_hi = umma_smem_desc(0, kPAtom, 1024);
+    const uint32_t tap_stride16 = (p.TW * 128) >> 4;
+    const uint32_t smem0 = smem_u32(smem);
+    const int taps = p.taps;
+    uint32_t it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+      const uint32_t st = it % kK2Stages;
+      const uint32_t ph = (it / kK2Stages) & 1;
+      mbar_wait(&full_bar[st], ph);
+      tc_fence_after();
+      const uint32_t sQ = smem0 + st * kK2Stage;
+      const uint32_t sP = sQ + 2 * kQAtom;
+      const uint64_t a0 = a_hi | (uint64_t)((sQ >> 4) & 0x3FFF);
+      const uint64_t b0 = b_hi | (uint64_t)((sP >> 4) & 0x3FFF);
+      if (elect_one()) {
+        for (int r = 0; r < taps; ++r) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // 128 pixels = 8 x K16; 16 pixel rows = 2048 bytes
-            // MN-major SWIZZLE_128B: LBO = byte stride between 64-channel atoms, SBO = stride between 8-pixel K groups
-            const uint64_t ad = umma_smem_desc(sQ + r * tap_stride + k * 2048, a_lbo, 1024);
-            const uint64_t bd = umma_smem_desc(sP + k * 2048, b_lbo, 1024);
-            umma_bf16(tmem_base + r * p.n_cols, ad, bd, idesc, (it | (uint32_t)k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 8; ++k) {  // 128 pixels = 8 x K16; 16 pixel rows = 2048 bytes = 128 x 16 B
+            umma_bf16(tmem_base + r * p.n_cols, a0 + (uint64_t)(r * tap_stride16 + k * 128), b0 + (uint64_t)(k * 128),
+                      idesc, (it | (uint32_t)k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[st]);
+        if (t == t_end - 1) umma_commit(tfull_bar);
       }
-      umma_commit(tfull_bar);
+      __syncwarp();
     }
+    if (t_end <= t_begin && elect_one()) umma_commit(tfull_bar);
     __syncwarp();
   } else {
     const uint32_t q = warp & 3;
