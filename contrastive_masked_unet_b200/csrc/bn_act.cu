@@ -293,19 +293,39 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int grid, 
 __global__ void __launch_bounds__(256) bn_relu_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                                       const float* __restrict__ shift, __nv_bfloat16* __restrict__ a,
                                                       size_t npix, int C) {
+  // the grid stride is a multiple of C/8, so a thread keeps ONE channel group: scale/shift live in registers and four
+  // independent 16-byte loads are in flight per thread
   const int cgs = C >> 3;
   const size_t total = npix * cgs;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int cg = i % cgs;
-    float f[8], sc[8], sh[8];
-    unpack8(reinterpret_cast<const uint4*>(y)[i], f);
-    *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale) + cg * 2);
-    *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale) + cg * 2 + 1);
-    *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift) + cg * 2);
-    *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift) + cg * 2 + 1);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = (int)(i % cgs);
+  float sc[8], sh[8];
+  *reinterpret_cast<float4*>(sc) = __ldg(reinterpret_cast<const float4*>(scale) + cg * 2);
+  *reinterpret_cast<float4*>(sc + 4) = __ldg(reinterpret_cast<const float4*>(scale) + cg * 2 + 1);
+  *reinterpret_cast<float4*>(sh) = __ldg(reinterpret_cast<const float4*>(shift) + cg * 2);
+  *reinterpret_cast<float4*>(sh + 4) = __ldg(reinterpret_cast<const float4*>(shift) + cg * 2 + 1);
+  const uint4* yv = reinterpret_cast<const uint4*>(y);
+  uint4* av = reinterpret_cast<uint4*>(a);
+  for (; i + 3 * stride < total; i += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldcs(yv + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+      av[i + u * stride] = pack8(f);
+    }
+  }
+  for (; i < total; i += stride) {
+    float f[8];
+    unpack8(__ldcs(yv + i), f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
-    reinterpret_cast<uint4*>(a)[i] = pack8(f);
+    av[i] = pack8(f);
   }
 }
 // one thread: a 2x2 pixel quad x 8 channels -> 4 activated vectors + 1 pooled vector
@@ -438,18 +458,33 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __nv_bfloat16* __rest
           if (kApply) reinterpret_cast<uint4*>(dy)[pixs[d] * cgs + cg] = pack8(o);
         }
       } else {
-        float yv[8], g[8], o[8];
-        unpack8(reinterpret_cast<const uint4*>(y)[u * cgs + cg], yv);
-        unpack8(reinterpret_cast<const uint4*>(da)[u * cgs + cg], g);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float z = fmaf(yv[k], sc[k], sh[k]);
-          const float dz = (z > 0.f) ? g[k] : 0.f;
-          const float xh = (yv[k] - mu[k]) * rs[k];
-          if (kApply) o[k] = sc[k] * (dz - k1[k] - xh * k2[k]);
-          else { a1[k] += dz; a2[k] += dz * xh; }
+        // two independent pixels per iteration (4 x 16-byte loads in flight per thread)
+        const size_t ustride = (size_t)gridDim.x * slots;
+        const bool two = (u + ustride) < units;
+        const uint4 ry0 = __ldcs(reinterpret_cast<const uint4*>(y) + u * cgs + cg);
+        const uint4 rg0 = __ldcs(reinterpret_cast<const uint4*>(da) + u * cgs + cg);
+        uint4 ry1 = ry0, rg1 = rg0;
+        if (two) {
+          ry1 = __ldcs(reinterpret_cast<const uint4*>(y) + (u + ustride) * cgs + cg);
+          rg1 = __ldcs(reinterpret_cast<const uint4*>(da) + (u + ustride) * cgs + cg);
         }
-        if (kApply) reinterpret_cast<uint4*>(dy)[u * cgs + cg] = pack8(o);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1 && !two) break;
+          float yv[8], g[8], o[8];
+          unpack8(half ? ry1 : ry0, yv);
+          unpack8(half ? rg1 : rg0, g);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float z = fmaf(yv[k], sc[k], sh[k]);
+            const float dz = (z > 0.f) ? g[k] : 0.f;
+            const float xh = (yv[k] - mu[k]) * rs[k];
+            if (kApply) o[k] = sc[k] * (dz - k1[k] - xh * k2[k]);
+            else { a1[k] += dz; a2[k] += dz * xh; }
+          }
+          if (kApply) reinterpret_cast<uint4*>(dy)[(u + (half ? ustride : 0)) * cgs + cg] = pack8(o);
+        }
+        u += ustride;   // consumed two units this iteration (the loop increment adds the other stride)
       }
     }
   }
@@ -579,7 +614,7 @@ int cmu_bn_finalize(const float* partial, int grid, int bn_tile, int c, double c
 
 int cmu_bn_relu_apply(const void* y, const float* scale, const float* shift, void* a, void* pooled, int n, int h, int w,
                       int c, void* stream) {
-  CMU_REQUIRE(c % 8 == 0, "bn_relu_apply: C must be a multiple of 8");
+  CMU_REQUIRE(c % 8 == 0 && 256 % (c / 8) == 0, "bn_relu_apply: C/8 must divide 256 (C = 8, 16, ..., 2048; got %d)", c);
   if (pooled != nullptr) {
     CMU_REQUIRE(h % 2 == 0 && w % 2 == 0, "bn_relu_apply: pooling needs even H, W");
     const size_t total = (size_t)n * (h / 2) * (w / 2) * (c / 8);

@@ -191,6 +191,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// shared-memory float reduction without a return value (a plain atomicAdd on a generic pointer compiles to a
+// generic-address ATOM)
+__device__ __forceinline__ void red_shared_add(float* p, float v) {
+  asm volatile("red.shared::cta.add.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -329,8 +329,8 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
             }
             column_sums(s1, lane);
             column_sums(s2, lane);
-            atomicAdd(&s_stats[j * 32 + lane], s1[0]);
-            atomicAdd(&s_stats[BN + j * 32 + lane], s2[0]);
+            red_shared_add(&s_stats[j * 32 + lane], s1[0]);
+            red_shared_add(&s_stats[BN + j * 32 + lane], s2[0]);
           }
         }
         fence_proxy_async_smem();
