@@ -15,56 +15,10 @@
 // MMAs of tile i+1.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "k1_common.cuh"
 #include "../../include/cmu_b200.h"
 
 namespace cmu {
-
-enum { MODE_CONV3 = 0, MODE_PLAIN = 1, MODE_CONVT_FPROP = 2, MODE_CONVT_DGRAD = 3 };
-
-constexpr int kK1Threads = 192;
-constexpr int kStagingBytes = 16384;  // one 128 x 64 bf16 output slab
-constexpr int kMaxStages = 8;
-constexpr int kSchedDepth = 4;
-constexpr int kSmemLimit = 232448;    // 227 KB per CTA
-
-struct K1Params {
-  CUtensorMap tmA0, tmA1, tmB, tmO0, tmO1;
-  int mode;
-  int N, H, W;      // pixel space of GEMM-M (output pixels; for convT: the low-resolution grid)
-  int c0, c1;       // channels of A source 0 / 1 (concat along K)
-  int n_total;      // GEMM N
-  int oc0;          // channels of output 0 (dual-output split; convT fprop: Cout)
-  int TW, TH, tw_shift;
-  int tiles_w, tiles_h, m_tiles, n_tiles;
-  int kc;           // number of 64-wide K chunks per tap
-  // shared-memory plan (host-computed): [n_stages x stage_bytes][stg_bufs x 16 KB staging][barriers][stats]
-  int a_bytes, b_bytes, b_off, stage_bytes, n_stages, stg_bufs;
-  int w_resident;   // 1: this CTA's whole weight slab (all taps x K chunks of its n-tile) is loaded ONCE into shared
-  int w_bytes;      //    memory and the pipeline streams activations only (small-weight layers)
-  unsigned int* sched;  // [n_tiles] m-tile counters, zeroed before the launch (dynamic tile scheduler)
-  const float* bias;
-  int bias_mod;
-  float* stats;     // [gridDim.x][2][BN] partial (sum, sum of squares) or nullptr
-};
-
-template <int OFF>
-__device__ __forceinline__ void bfly(float (&v)[32], uint32_t lane) {
-  const bool up = (lane & OFF) != 0;
-#pragma unroll
-  for (int i = 0; i < OFF; ++i) {
-    const float send = up ? v[i] : v[i + OFF];
-    const float keep = up ? v[i + OFF] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-  }
-}
-// After the call, lane L holds in v[0] the sum over the 32 lanes of their v[L].
-__device__ __forceinline__ void column_sums(float (&v)[32], uint32_t lane) {
-  bfly<16>(v, lane);
-  bfly<8>(v, lane);
-  bfly<4>(v, lane);
-  bfly<2>(v, lane);
-  bfly<1>(v, lane);
-}
 
 // Tile scheduling: every CTA owns ONE n-tile (blockIdx % n_tiles; its BatchNorm partial sums live in one smem slot)
 // and pulls m-tiles of that n-tile from a global atomic counter.  The producer thread fetches tile indices and
@@ -502,6 +456,17 @@ static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int 
       if (make_act_map(&p.tmO1, out1, N, H, W, oc1, p.TW, p.TH)) return 1;
     } else {
       p.tmO1 = p.tmO0;
+    }
+  }
+  // CTA-pair kernel (tcgen05 cta_group::2) for the large tensor-bound layers
+  {
+    int pair_grid = 0, pair_bn = 0;
+    K1Params pp = p;
+    if (run_k1_pair(pp, wpk, ktot, stream, &pair_grid, &pair_bn)) return 1;
+    if (pair_grid > 0) {
+      if (stats_grid) *stats_grid = pair_grid;
+      if (stats_bn) *stats_bn = pair_bn;
+      return 0;
     }
   }
   // shared-memory plan

@@ -27,7 +27,8 @@ int cmu_version(void);
 int cmu_device_check(void);               /* current device must be sm_100 */
 long long cmu_launch_count(void);         /* kernels launched by this library so far (this process) */
 int cmu_debug_set(int key, int value);    /* 0: 1 = CUDA-core cross-check path for the conv GEMMs (tests only)
-                                             1: 64 = force 64-wide N tiles; 3: 1 = static tile schedule (A/B); 4: 1 = no resident weights (A/B) */
+                                             1: 64 = force 64-wide N tiles; 3: 1 = static tile schedule (A/B); 4: 1 = no resident weights (A/B);
+                                             5: 1 = no CTA-pair kernel (A/B); 6: 1 = pair kernel with N = 128 only */
 
 /* ---- a1  patch-mask generator: CMU/backbones/UNet_encoder.py:106-139 (create_random_patch_mask) ------------
  * d_state: uint32[cmu_mask_state_words()] = MT19937 key[624] + position, same content as numpy's
@@ -58,7 +59,7 @@ int cmu_conv3x3_c1_wgrad(const float* x, const unsigned char* mask0, const void*
 /* conv3x3 pad 1 as tcgen05 implicit GEMM.  (x0|x1) = channel concat of two act tensors (munet_neck.py:48; x1 may be
  * NULL).  The conv bias is NOT applied (it cancels inside the train-mode BN that always follows; cmu_bn_finalize
  * folds it into running_mean / the eval shift).  stats_partial: float[*stats_grid][2][*stats_bn] per-CTA
- * (sum, sumsq) of the fp32 accumulators; size it with cmu_conv_max_grid() * 2 * 128. */
+ * (sum, sumsq) of the fp32 accumulators; size it with cmu_conv_max_grid() * 2 * max(128, Cout). */
 int cmu_conv_max_grid(void);
 int cmu_conv3x3_fprop(const void* x0, int c0, const void* x1, int c1, int n, int h, int w, const void* w_packed, int cout,
                       void* y, float* stats_partial, int* h_stats_grid, int* h_stats_bn, void* stream);

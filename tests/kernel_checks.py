@@ -519,6 +519,10 @@ CHECKS = {
     'conv3x3_cat_64+64_64_resident': lambda: check_conv3x3(6, 128, 128, 64, 64, 64, seed=8),
     'conv3x3_64_128_resident': lambda: check_conv3x3(6, 128, 128, 64, 0, 128, seed=9),
     'convT_128_64_resident': lambda: check_convT(8, 64, 128, 128, 64, seed=14),
+    'conv3x3_pair_128_128': lambda: check_conv3x3(6, 128, 128, 128, 0, 128, seed=30),
+    'conv3x3_pair_cat_128+128_256': lambda: check_conv3x3(8, 96, 96, 128, 128, 256, seed=31),
+    'conv3x3_pair_odd_tiles_256_256': lambda: check_conv3x3(7, 88, 72, 256, 0, 256, seed=32),
+    'conv3x3_pair_64_128': lambda: check_conv3x3(6, 128, 128, 64, 0, 128, seed=33),
     'conv3x3_fprop_only_64_64': lambda: check_conv3x3_fprop_only(2, 24, 40, 64, 0, 64),
     'conv3x3_wgrad_only_64_64': lambda: check_conv3x3_wgrad_only(2, 24, 40, 64, 0, 64),
     'conv3x3_wgrad_only_128_128': lambda: check_conv3x3_wgrad_only(2, 16, 16, 128, 0, 128, seed=1),
