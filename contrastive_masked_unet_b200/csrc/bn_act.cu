@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __nv_bfloat16* __rest
       } else {
         // two independent pixels per iteration (4 x 16-byte loads in flight per thread)
         const size_t ustride = (size_t)gridDim.x * slots;
-        const bool two = (u + ustride) < units;
+        const bool two = !kApply && (u + ustride) < units;   // (the apply pass is store-bound: no gain, more registers)
         const uint4 ry0 = __ldcs(reinterpret_cast<const uint4*>(y) + u * cgs + cg);
         const uint4 rg0 = __ldcs(reinterpret_cast<const uint4*>(da) + u * cgs + cg);
         uint4 ry1 = ry0, rg1 = rg0;

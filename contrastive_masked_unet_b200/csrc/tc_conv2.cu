@@ -281,8 +281,9 @@ int run_k1_pair(K1Params& p, const void* wpk, int ktot, cudaStream_t stream, int
   *used = 0;
   if (debug_knob(5) == 1) return 0;
   if (p.mode != MODE_CONV3 && p.mode != MODE_PLAIN) return 0;
-  if (p.n_total % 128 != 0 || p.m_tiles < 2 * num_sms()) return 0;
-  const int BN = (p.n_total % 256 == 0 && debug_knob(6) != 1) ? 256 : 128;
+  if (p.m_tiles < 2 * num_sms()) return 0;
+  if (p.n_total % 128 != 0 && debug_knob(7) == 1) return 0;   // A/B: 64-wide layers on the 1-CTA kernel
+  const int BN = (p.n_total % 256 == 0 && debug_knob(6) != 1) ? 256 : (p.n_total % 128 == 0 ? 128 : 64);
   p.n_tiles = p.n_total / BN;
   // weight tensor map with a BN/2-row box
   {
@@ -313,7 +314,9 @@ int run_k1_pair(K1Params& p, const void* wpk, int ktot, cudaStream_t stream, int
   const int grid = 2 * n_clusters;
   *used = grid;   // number of statistic partial rows
   *used_bn = BN;
-  return BN == 256 ? launch_pair<256>(p, grid, smem_bytes, stream) : launch_pair<128>(p, grid, smem_bytes, stream);
+  if (BN == 256) return launch_pair<256>(p, grid, smem_bytes, stream);
+  if (BN == 128) return launch_pair<128>(p, grid, smem_bytes, stream);
+  return launch_pair<64>(p, grid, smem_bytes, stream);
 }
 
 }  // namespace cmu

@@ -523,6 +523,8 @@ CHECKS = {
     'conv3x3_pair_cat_128+128_256': lambda: check_conv3x3(8, 96, 96, 128, 128, 256, seed=31),
     'conv3x3_pair_odd_tiles_256_256': lambda: check_conv3x3(7, 88, 72, 256, 0, 256, seed=32),
     'conv3x3_pair_64_128': lambda: check_conv3x3(6, 128, 128, 64, 0, 128, seed=33),
+    'conv3x3_pair_64_64': lambda: check_conv3x3(6, 128, 128, 64, 0, 64, seed=34),
+    'conv3x3_pair_cat_64+64_64': lambda: check_conv3x3(5, 136, 120, 64, 64, 64, seed=35),
     'conv3x3_fprop_only_64_64': lambda: check_conv3x3_fprop_only(2, 24, 40, 64, 0, 64),
     'conv3x3_wgrad_only_64_64': lambda: check_conv3x3_wgrad_only(2, 24, 40, 64, 0, 64),
     'conv3x3_wgrad_only_128_128': lambda: check_conv3x3_wgrad_only(2, 16, 16, 128, 0, 128, seed=1),
