@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __nv_bfloat16* __rest
           }
           if (kApply) reinterpret_cast<uint4*>(dy)[(u + (half ? ustride : 0)) * cgs + cg] = pack8(o);
         }
-        u += ustride;   // consumed two units this iteration (the loop increment adds the other stride)
+        if (two) u += ustride;   // consumed two units this iteration (the loop increment adds the other stride)
       }
     }
   }
