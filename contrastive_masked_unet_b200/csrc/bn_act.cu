@@ -237,13 +237,24 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restr
   __syncthreads();
   for (int i = threadIdx.x; i < kC1Cout * 9; i += blockDim.x) partial[(size_t)blockIdx.x * kC1Cout * 9 + i] = sred[i];
 }
-__global__ void reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out, int rows, int cols,
-                                   int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+// out[c] (+)= sum_r partial[r][c].  256 threads = 32 columns x 8 row lanes (coalesced 128-byte row segments, 8 rows in
+// flight per column), fp64 accumulation, fixed summation order.
+__global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                          int rows, int cols, int accumulate) {
+  __shared__ double sred[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   double a = 0.0;
-  for (int r = 0; r < rows; ++r) a += partial[(size_t)r * cols + c];
-  out[c] = accumulate ? out[c] + (float)a : (float)a;
+  if (c < cols)
+    for (int r = ry; r < rows; r += 8) a += partial[(size_t)r * cols + c];
+  sred[ry][cx] = a;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sred[k][cx];
+    out[c] = accumulate ? out[c] + (float)t : (float)t;
+  }
 }
 
 // ---------------------------------------------------------------------------------- BN finalize
@@ -251,23 +262,38 @@ __global__ void reduce_rows_kernel(const float* __restrict__ partial, float* __r
 // Train: mean/var from the batch (biased var for normalisation, unbiased for running_var); the conv bias is not
 // applied in the data path (it cancels inside train-mode BN) but it shifts the batch mean that running_mean tracks.
 // Eval: scale/shift from the running statistics (bias folded into the shift).
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int grid, int bn_tile, int C, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta,
-                                   const float* __restrict__ conv_bias, float* running_mean, float* running_var,
-                                   float momentum, float eps, int training, float* __restrict__ scale,
-                                   float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int grid, int bn_tile, int C,
+                                                          double count, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ conv_bias,
+                                                          float* running_mean, float* running_var, float momentum, float eps,
+                                                          int training, float* __restrict__ scale, float* __restrict__ shift,
+                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  // 256 threads = 32 channels x 8 row lanes; the per-CTA partial rows are summed in a fixed order in fp64
+  __shared__ double sred[2][8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double s1 = 0.0, s2 = 0.0;
+  if (training && c < C) {
+    const int n_tiles = C / bn_tile;
+    const int nt = c / bn_tile, j = c % bn_tile;
+    for (int b = nt + ry * n_tiles; b < grid; b += 8 * n_tiles) {
+      s1 += partial[((size_t)b * 2 + 0) * bn_tile + j];
+      s2 += partial[((size_t)b * 2 + 1) * bn_tile + j];
+    }
+  }
+  sred[0][ry][cx] = s1;
+  sred[1][ry][cx] = s2;
+  __syncthreads();
+  if (ry != 0 || c >= C) return;
   const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
   const float cb = conv_bias ? conv_bias[c] : 0.f;
   float mean, rstd;
   if (training) {
-    const int n_tiles = C / bn_tile;
-    const int nt = c / bn_tile, j = c % bn_tile;
-    double s1 = 0.0, s2 = 0.0;
-    for (int b = nt; b < grid; b += n_tiles) {
-      s1 += partial[((size_t)b * 2 + 0) * bn_tile + j];
-      s2 += partial[((size_t)b * 2 + 1) * bn_tile + j];
+    s1 = s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s1 += sred[0][k][cx];
+      s2 += sred[1][k][cx];
     }
     const double m = s1 / count;
     double var = s2 / count - m * m;
@@ -594,7 +620,7 @@ int cmu_conv3x3_c1_wgrad(const float* x, const unsigned char* mask0, const void*
   const int c1_shmem = 3 * (kC1MaxW + 2) * (int)sizeof(float);
   conv_c1_wgrad_kernel<<<grid, 256, c1_shmem, (cudaStream_t)stream>>>(x, mask0, (const __nv_bfloat16*)dy, partial, n, h, wd);
   CMU_LAUNCH_CHECK();
-  reduce_rows_kernel<<<ceil_div(kC1Cout * 9, 128), 128, 0, (cudaStream_t)stream>>>(partial, dw, grid, kC1Cout * 9,
+  reduce_rows_kernel<<<ceil_div(kC1Cout * 9, 32), 256, 0, (cudaStream_t)stream>>>(partial, dw, grid, kC1Cout * 9,
                                                                                    accumulate);
   CMU_LAUNCH_CHECK();
   return 0;
@@ -605,7 +631,7 @@ int cmu_bn_finalize(const float* partial, int grid, int bn_tile, int c, double c
                     float eps, int training, float* scale, float* shift, float* mean, float* rstd, void* stream) {
   CMU_REQUIRE(!training || (partial != nullptr && grid > 0 && bn_tile > 0 && c % bn_tile == 0), "bn_finalize: bad partial layout");
   CMU_REQUIRE(training || (running_mean && running_var), "bn_finalize: eval mode needs running statistics");
-  bn_finalize_kernel<<<ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(partial, grid, bn_tile, c, count, gamma, beta,
+  bn_finalize_kernel<<<ceil_div(c, 32), 256, 0, (cudaStream_t)stream>>>(partial, grid, bn_tile, c, count, gamma, beta,
                                                                         conv_bias, running_mean, running_var, momentum,
                                                                         eps, training, scale, shift, mean, rstd);
   CMU_LAUNCH_CHECK();
@@ -635,7 +661,7 @@ int cmu_colsum_bf16(const void* x, long long rows, int c, float* partial, float*
   colsum_bf16_kernel<<<grid, 256, c * sizeof(float), (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (size_t)rows, c,
                                                                             partial);
   CMU_LAUNCH_CHECK();
-  reduce_rows_kernel<<<ceil_div(c, 128), 128, 0, (cudaStream_t)stream>>>(partial, out, grid, c, 0);
+  reduce_rows_kernel<<<ceil_div(c, 32), 256, 0, (cudaStream_t)stream>>>(partial, out, grid, c, 0);
   CMU_LAUNCH_CHECK();
   return 0;
 }
@@ -663,7 +689,7 @@ int cmu_bn_relu_bwd(const void* da, const void* dpool, const void* y, const floa
                                                           partial, nullptr, n, h, w, c);
   }
   CMU_LAUNCH_CHECK();
-  reduce_rows_kernel<<<ceil_div(2 * c, 128), 128, 0, st>>>(partial, sums, grid, 2 * c, 0);
+  reduce_rows_kernel<<<ceil_div(2 * c, 32), 256, 0, st>>>(partial, sums, grid, 2 * c, 0);
   CMU_LAUNCH_CHECK();
   if (dpool != nullptr)
     bn_bwd_kernel<true, true><<<grid * 4, 256, 0, st>>>(pda, pdp, py, scale, shift, mean, rstd, sums, inv_count, nullptr,

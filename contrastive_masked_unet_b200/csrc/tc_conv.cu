@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
   int* sched_tile = reinterpret_cast<int*>(wfull_bar + 1);  // [kSchedDepth]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sched_tile + kSchedDepth);
   float* s_stats = reinterpret_cast<float*>(bars + 40);  // [2][BN]
+  float* s_bias = s_stats + 2 * BN;                      // [BN] bias of this CTA's n-tile (broadcast reads in the epilogue)
   constexpr uint32_t kTmemCols = 2 * BN;
 
   const uint32_t warp = threadIdx.x >> 5;
@@ -68,6 +69,8 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
     tma_prefetch_desc(&p.tmO0);
   }
   for (int i = threadIdx.x; i < 2 * BN; i += kK1Threads) s_stats[i] = 0.f;
+  if (p.bias != nullptr)
+    for (int i = threadIdx.x; i < BN; i += kK1Threads) s_bias[i] = p.bias[((blockIdx.x % p.n_tiles) * BN + i) % p.bias_mod];
   if (warp == 1) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
@@ -257,9 +260,15 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
           if (p.bias != nullptr) {
-            const int cb = (n0 + j * 32) % p.bias_mod;
+            const float4* sb = reinterpret_cast<const float4*>(s_bias + j * 32);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + cb + i);
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = sb[i];
+              v[4 * i + 0] += b4.x;
+              v[4 * i + 1] += b4.y;
+              v[4 * i + 2] += b4.z;
+              v[4 * i + 3] += b4.w;
+            }
           }
           // bf16 pack + swizzled staging store (16-byte chunk index XOR (row & 7): TMA SWIZZLE_128B pattern)
           uint8_t* rowp = stg + row * 128;
@@ -474,7 +483,7 @@ static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int 
   p.b_bytes = ((mode == MODE_CONV3) ? 3 : 1) * BN * 128;
   p.b_off = (p.a_bytes + 1023) & ~1023;
   p.stage_bytes = p.b_off + p.b_bytes;
-  const int fixed = 1024 /*align*/ + 320 /*barriers*/ + 2 * BN * 4 + 64;
+  const int fixed = 1024 /*align*/ + 320 /*barriers*/ + 3 * BN * 4 /*stats + bias*/ + 64;
   // small-weight layers: keep the n-tile's whole weight slab resident, stream activations only
   const int w_all = p.kc * ((mode == MODE_CONV3) ? 3 : 1) * p.b_bytes;   // all taps x K chunks of one n-tile
   p.w_resident = 0;

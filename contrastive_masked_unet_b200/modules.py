@@ -462,7 +462,8 @@ class CM_UNet(nn.Module):
             p.requires_grad = False
         # one numpy-compatible mask stream shared by both encoders, online first (quirk Q2)
         self.target_backbone.mask_stream = self.backbone.mask_stream
-        self.backbone.mask_stream.pair_mode = True
+        import os
+        self.backbone.mask_stream.pair_mode = os.environ.get('CMU_NO_MASK_PREFETCH') != '1'   # A/B switch
         # Q3: the reference draws a fresh, untrained Conv2d(1024,256,1) in every forward_train (cmunet.py:128).
         # persistent_reduce=True (opt-in) keeps the first draw.
         self.persistent_reduce = persistent_reduce
