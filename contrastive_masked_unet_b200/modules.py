@@ -469,6 +469,9 @@ class CM_UNet(nn.Module):
         self.persistent_reduce = persistent_reduce
         self._reduce = None
         self._ema_table = None
+        import os
+        self.multi_stream = os.environ.get('CMU_SINGLE_STREAM') != '1'
+        self._aux_streams = None
 
     # ----------------------------------------------------------------------------------- reference API
     def init_weights(self):
@@ -515,22 +518,47 @@ class CM_UNet(nn.Module):
             self._reduce = (w, conv.bias.detach().to(device).float().contiguous())
         return self._reduce
 
+    def _target_branch(self, img, img_t):
+        """Frozen target path (no grad): target encoder -> fresh 1x1 reduce (Q3) -> NCHW flatten -> target projector."""
+        latent_t, _, _ = self.target_backbone(img_t)
+        rw, rb = self._reduce_params(img.device)
+        lt = ops.conv1x1_fprop(Fn._nhwc(Fn.to_act(latent_t)), rw, rb)          # (B,h,w,256) act
+        b, h, w, c = lt.shape
+        flat = torch.empty(b, 1, img.shape[-2], img.shape[-1], dtype=torch.float32, device=img.device)
+        assert c * h * w == img.shape[-2] * img.shape[-1]
+        lib.cmu_nhwc_to_nchw_f32(lt.data_ptr(), flat.data_ptr(), b, h * w, c, ops._stream())   # :130 NCHW flatten
+        return self.target_projector(flat)                     # mean over the single channel is the identity (:131)
+
     def forward_train(self, img, img_t=None, **kwargs):
+        """cmunet.py:108-135.  The three branches that only meet in the head -- target path, pixel decoder, feature
+        decoder + projector -- are enqueued on three CUDA streams, so the HBM-bound BatchNorm / element-wise kernels of
+        one branch run under the tensor-core kernels of another (autograd replays each branch's backward on its own
+        stream).  Host-side call order (mask stream: online first, then target; CPU RNG draw of Q3) is unchanged."""
         ops._need_cuda(img)
         latent_s, mask_s, skip_s = self.backbone(img)
-        with torch.no_grad():
-            latent_t, _, _ = self.target_backbone(img_t)
+        if not self.multi_stream:
+            with torch.no_grad():
+                proj_t = self._target_branch(img, img_t)
+            pred_pixel = self.pixel_decoder(latent_s, skip_s)
+            pred_feature = self.feature_decoder(latent_s, skip_s)
+            proj_s = self.projector(Fn.ChannelMean2Fn.apply(pred_feature))
+            return self.head(img, pred_pixel[:, 1], mask_s, proj_s, proj_t)
+        main = torch.cuda.current_stream()
+        if self._aux_streams is None or self._aux_streams[0].device != img.device:
+            self._aux_streams = (torch.cuda.Stream(device=img.device), torch.cuda.Stream(device=img.device))
+        s_tgt, s_feat = self._aux_streams
+        s_tgt.wait_stream(main)
+        s_feat.wait_stream(main)
+        with torch.cuda.stream(s_tgt), torch.no_grad():
+            proj_t = self._target_branch(img, img_t)
+        with torch.cuda.stream(s_feat):
+            pred_feature = self.feature_decoder(latent_s, skip_s)
+            proj_s = self.projector(Fn.ChannelMean2Fn.apply(pred_feature))
         pred_pixel = self.pixel_decoder(latent_s, skip_s)
-        pred_feature = self.feature_decoder(latent_s, skip_s)
-        proj_s = self.projector(Fn.ChannelMean2Fn.apply(pred_feature))
-        with torch.no_grad():
-            rw, rb = self._reduce_params(img.device)
-            lt = ops.conv1x1_fprop(Fn._nhwc(Fn.to_act(latent_t)), rw, rb)          # (B,h,w,256) act
-            b, h, w, c = lt.shape
-            flat = torch.empty(b, 1, img.shape[-2], img.shape[-1], dtype=torch.float32, device=img.device)
-            assert c * h * w == img.shape[-2] * img.shape[-1]
-            lib.cmu_nhwc_to_nchw_f32(lt.data_ptr(), flat.data_ptr(), b, h * w, c, ops._stream())   # :130 NCHW flatten
-            proj_t = self.target_projector(flat)                   # mean over the single channel is the identity (:131)
+        main.wait_stream(s_tgt)
+        main.wait_stream(s_feat)
+        proj_t.record_stream(main)
+        proj_s.record_stream(main)
         return self.head(img, pred_pixel[:, 1], mask_s, proj_s, proj_t)
 
     def forward(self, img, mode='loss', **kwargs):
@@ -544,6 +572,7 @@ class CM_UNet(nn.Module):
     def __getstate__(self):
         d = dict(self.__dict__)
         d['_ema_table'] = None
+        d['_aux_streams'] = None
         d['_reduce'] = None if not self.persistent_reduce else d['_reduce']
         return d
 
