@@ -77,3 +77,25 @@ def test_cpu_tensor_raises_no_fallback():
     net = C.UNet().cuda()
     with pytest.raises(C.CmuError):
         net(torch.rand(1, 32, 32))
+
+
+def test_pretrain_step_S512_B2_vs_golden_losses():
+    """512 x 512 (the benchmark size) against the golden minted from the S-generalised reference at B=2.  With two rows
+    the projection-head BatchNorm is degenerate (x_hat = +-1), so loss_ct is only sanity-checked; loss_rc is exact to
+    bf16 tolerance."""
+    _gpu()
+    from tests import model_checks as M
+    g = M.golden_pretrain(512, 2)
+    rep = M.pretrain_parity(512, 2, golden=None, autocast_ref=False, grad_cos=-1.0)
+    assert abs(rep['loss_rc'][0] - g['loss_rc']) <= 1e-2 * g['loss_rc'], rep['loss_rc']
+    assert abs(rep['loss_rc'][0] - rep['loss_rc'][1]) <= 1e-2 * rep['loss_rc'][1]
+    assert abs(rep['loss_ct'][0] - g['loss_ct']) <= 0.25 * g['loss_ct'] + 0.02, (rep['loss_ct'], g['loss_ct'])
+    assert rep['mask_mismatch'] == 0 and rep['ema_max_abs_err'] <= 1e-6
+
+
+def test_finetune_S1024_config5_shape():
+    """BASELINE.json configs[4] resolution (1024 x 1024) on one GPU, batch 1: forward/backward parity with the oracle."""
+    _gpu()
+    from tests import model_checks as M
+    rep = M.finetune_parity(1, 1024, seed=3)
+    assert not rep['fails'], (rep['fails'][:8], {k: v for k, v in rep.items() if k != 'fails'})
