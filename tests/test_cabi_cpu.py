@@ -109,3 +109,27 @@ def test_mask_stream_numpy_handover():
     ms.set_numpy_state(np.random.get_state(), device='cpu')
     st = ms.get_numpy_state()
     assert st[2] == 624 and (st[1] == np.random.get_state()[1]).all()
+
+
+def test_checkpoint_handoff_pretrain_to_finetune(tmp_path):
+    """Finetuning/train.py:262-273: a pretraining checkpoint in mmengine layout loads into the fine-tune UNet."""
+    from contrastive_masked_unet_b200.checkpoint import load_pretrained_into_unet, save_pretrain_checkpoint
+    torch.manual_seed(3)
+    m = C.build(C.cmunet_config(64))
+    m.init_weights()
+    path = str(tmp_path / 'epoch_1.pth')
+    ck = save_pretrain_checkpoint(m, path)
+    assert 'mmengine_version' in ck['meta'] and any(k.startswith('backbone.') for k in ck['state_dict'])
+    torch.manual_seed(4)
+    u = C.UNet()
+    last_w = u.conv_last.weight.detach().clone()
+    res = load_pretrained_into_unet(u, path)
+    assert set(res.missing_keys) == {'conv_last.weight', 'conv_last.bias'}          # dropped on purpose (:271-272)
+    assert torch.equal(u.conv_last.weight, last_w)
+    assert torch.equal(u.down_conv3.double_conv.double_conv[0].weight, m.backbone.down_conv3.double_conv.double_conv[0].weight)
+    assert torch.equal(u.up_conv2.up_sample.weight, m.pixel_decoder.up_conv2.up_sample.weight)
+    assert torch.equal(u.double_conv.double_conv[4].running_var, m.backbone.double_conv.double_conv[4].running_var)
+    # and the same file loads in the oracle (== reference layout) UNet
+    ou = O.OracleUNet()
+    load_pretrained_into_unet(ou, path)
+    assert torch.equal(ou.up_conv4.double_conv.double_conv[3].weight, m.pixel_decoder.up_conv4.double_conv.double_conv[3].weight)
