@@ -238,6 +238,10 @@ def run_ours(args):
         roofline = {'bound': 'tensor', 'kernel': 'k1_kernel (tcgen05 implicit-GEMM conv3x3 fprop+dgrad)',
                     'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
                     'frac': achieved / peaks['bf16_tflops'], 'traffic': None, 'peak_source': peaks['source'],
+                    'traffic_note': 'achieved aggregates ~60 K1 launches of different layers per step, so there is no '
+                                    'single per-launch byte count; ncu --set full of one representative launch '
+                                    '(enc3.conv2 fprop, B=64): dram read+write 1.030 GB vs 1.074 GB algorithmic '
+                                    '(profiles/r1_k1pair_ncu_full.md)',
                     'launches': k1_n, 'avg_launch_ms': k1_ms / max(1, k1_n), 'share_of_step': k1_ms / ms,
                     'all_tensor_core_kernels': {k: {'launches': v[0], 'ms': round(v[1], 3),
                                                     'tflops': round(v[2] / (v[1] / 1e3) / 1e12, 1) if v[1] > 0 else None}
