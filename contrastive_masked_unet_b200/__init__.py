@@ -7,4 +7,6 @@ from .modules import (CM_UNet, CMUNetPretrainHead, DoubleConv, DownBlock, MaskSt
                       try_register_mmengine)
 from .finetune import CrossEntropyLoss, DiceLoss, IoU, Loss, Metric, MultipliedLoss, SumOfLosses, UNet  # noqa: F401
 
+from .moco import Moco_v2, MocoUNetEncoder  # noqa: F401
+
 __version__ = '0.1.0'

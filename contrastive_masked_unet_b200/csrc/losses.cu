@@ -507,3 +507,187 @@ int cmu_nhwc_to_nchw_f32(const void* x, float* y, int n, int hw, int c, void* st
 }
 
 }  // extern "C"
+
+// =========================================================================================== MoCo-v2 queue head
+// (BASELINE.json configs[3]; Pretraining/MoCo/pl_bolts/models/self_supervised/moco/moco2_module.py:224-270,160-175)
+// logits = [q.k, q.Queue] / T, CE(label 0).  The N x K negative logits come from the tcgen05 1x1 kernel
+// (Queue rows as "pixels", the normalised queries as the weight matrix) as lt[K][N] bf16; this kernel does the
+// row-wise online softmax over the K+1 logits of each query, writes the probabilities P[K][N] (bf16, the operand of
+// the tensor-core dq GEMM  dq_neg = P^T Queue) and the positive-logit terms.
+namespace cmu {
+
+// spatial mean of an NHWC bf16 tensor: out[n][c] = mean_p x[n][p][c]   (moco_data_module.py:65 torch.mean(x,[2,3]))
+__global__ void __launch_bounds__(256) spatial_mean_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out,
+                                                           int hw, int C) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const __nv_bfloat16* p = x + (size_t)n * hw * C + c;
+  float a = 0.f;
+  for (int i = 0; i < hw; ++i) a += __bfloat162float(p[(size_t)i * C]);
+  out[(size_t)n * C + c] = a / (float)hw;
+}
+__global__ void __launch_bounds__(256) spatial_mean_bwd_kernel(const float* __restrict__ dout, __nv_bfloat16* __restrict__ dx,
+                                                               int hw, int C, size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    const size_t n = i / ((size_t)hw * C);
+    dx[i] = __float2bfloat16_rn(dout[n * C + c] / (float)hw);
+  }
+}
+
+// one block per query n: online softmax over {l_pos} U {lt[j][n]}.
+// lt: [K][N] bf16 = q_hat . queue_j (NOT yet divided by T); out: loss_rows[n], ppos[n] (probability of the positive),
+// P[j][n] bf16 = softmax probability of negative j scaled by `pscale` (= 1 / (N*T), so that P^T Queue is dq_hat directly).
+__global__ void __launch_bounds__(256) moco_softmax_kernel(const __nv_bfloat16* __restrict__ lt, const float* __restrict__ lpos,
+                                                           int K, int N, float inv_t, float pscale,
+                                                           float* __restrict__ loss_rows, float* __restrict__ ppos,
+                                                           __nv_bfloat16* __restrict__ P) {
+  __shared__ float sred[8];
+  __shared__ float s_m, s_l;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float lp = lpos[n] * inv_t;
+  float m = lp;
+  for (int j = tid; j < K; j += 256) m = fmaxf(m, __bfloat162float(lt[(size_t)j * N + n]) * inv_t);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) sred[wid] = m;
+  __syncthreads();
+  m = sred[0];
+  for (int k = 1; k < 8; ++k) m = fmaxf(m, sred[k]);
+  __syncthreads();
+  float l = 0.f;
+  for (int j = tid; j < K; j += 256) l += __expf(__bfloat162float(lt[(size_t)j * N + n]) * inv_t - m);
+  l = warp_sum(l);
+  if (lane == 0) sred[wid] = l;
+  __syncthreads();
+  if (tid == 0) {
+    float t = __expf(lp - m);
+    for (int k = 0; k < 8; ++k) t += sred[k];
+    s_m = m;
+    s_l = t;
+    loss_rows[n] = (m + logf(t)) - lp;
+    ppos[n] = __expf(lp - m) / t;
+  }
+  __syncthreads();
+  if (P != nullptr) {
+    const float inv_l = pscale / s_l, mm = s_m;
+    for (int j = tid; j < K; j += 256)
+      P[(size_t)j * N + n] = __float2bfloat16_rn(__expf(__bfloat162float(lt[(size_t)j * N + n]) * inv_t - mm) * inv_l);
+  }
+}
+// q_hat = q/|q| (bf16 copy for the GEMM), l_pos[n] = <q_hat, k_n>
+__global__ void __launch_bounds__(256) moco_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, int D,
+                                                        __nv_bfloat16* __restrict__ qh16, float* __restrict__ qh,
+                                                        float* __restrict__ qnorm, float* __restrict__ lpos) {
+  __shared__ float sred[8], sred2[8];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  float ss = 0.f;
+  for (int d = tid; d < D; d += 256) { const float v = q[(size_t)n * D + d]; ss += v * v; }
+  ss = warp_sum(ss);
+  if ((tid & 31) == 0) sred[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < 8; ++i) tot += sred[i];
+  const float nrm = fmaxf(sqrtf(tot), 1e-12f);
+  float dp = 0.f;
+  for (int d = tid; d < D; d += 256) {
+    const float v = q[(size_t)n * D + d] / nrm;
+    qh[(size_t)n * D + d] = v;
+    qh16[(size_t)n * D + d] = __float2bfloat16_rn(v);
+    dp += v * k[(size_t)n * D + d];
+  }
+  dp = warp_sum(dp);
+  if ((tid & 31) == 0) sred2[tid >> 5] = dp;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += sred2[i];
+    lpos[n] = t;
+    qnorm[n] = nrm;
+  }
+}
+// dq = (I - q_hat q_hat^T)/|q| * g,  g = dq_neg + (ppos - 1)/(N*T) * k      (all per row)
+__global__ void __launch_bounds__(256) moco_dq_kernel(const float* __restrict__ dq_neg, const float* __restrict__ k,
+                                                      const float* __restrict__ qh, const float* __restrict__ qnorm,
+                                                      const float* __restrict__ ppos, int D, float coef,
+                                                      float* __restrict__ dq) {
+  __shared__ float sred[8];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const float cp = (ppos[n] - 1.f) * coef;
+  float pg = 0.f;
+  for (int d = tid; d < D; d += 256) {
+    const float g = dq_neg[(size_t)n * D + d] + cp * k[(size_t)n * D + d];
+    pg += qh[(size_t)n * D + d] * g;
+  }
+  pg = warp_sum(pg);
+  if ((tid & 31) == 0) sred[tid >> 5] = pg;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < 8; ++i) tot += sred[i];
+  const float inv = 1.f / qnorm[n];
+  for (int d = tid; d < D; d += 256) {
+    const float g = dq_neg[(size_t)n * D + d] + cp * k[(size_t)n * D + d];
+    dq[(size_t)n * D + d] = (g - qh[(size_t)n * D + d] * tot) * inv;
+  }
+}
+// queue rows [ptr, ptr+n) <- keys (bf16 row copy) and queue_ref[:, ptr+i] <- keys[i] (reference (D,K) fp32 layout)
+__global__ void queue_enqueue_kernel(const float* __restrict__ keys, int n, int D, int K, int ptr,
+                                     __nv_bfloat16* __restrict__ qrows, float* __restrict__ qref) {
+  const size_t total = (size_t)n * D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int d = i % D;
+    const int r = (ptr + (int)(i / D)) % K;
+    const float v = keys[i];
+    qrows[(size_t)r * D + d] = __float2bfloat16_rn(v);
+    if (qref != nullptr) qref[(size_t)d * K + r] = v;
+  }
+}
+
+}  // namespace cmu
+
+extern "C" {
+
+int cmu_spatial_mean(const void* x, float* out, int n, int hw, int c, void* stream) {
+  dim3 grid(ceil_div(c, 256), n);
+  spatial_mean_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, out, hw, c);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+int cmu_spatial_mean_bwd(const float* dout, void* dx, int n, int hw, int c, void* stream) {
+  const size_t total = (size_t)n * hw * c;
+  spatial_mean_bwd_kernel<<<grid_for(total, 256, 8), 256, 0, (cudaStream_t)stream>>>(dout, (__nv_bfloat16*)dx, hw, c, total);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+int cmu_moco_prep(const float* q, const float* k, int n, int d, void* qh16, float* qh, float* qnorm, float* lpos,
+                  void* stream) {
+  moco_prep_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(q, k, d, (__nv_bfloat16*)qh16, qh, qnorm, lpos);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+int cmu_moco_softmax(const void* lt, const float* lpos, int k, int n, float temperature, float* loss_rows, float* loss,
+                     float* ppos, void* p, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  moco_softmax_kernel<<<n, 256, 0, st>>>((const __nv_bfloat16*)lt, lpos, k, n, 1.f / temperature,
+                                         1.f / ((float)n * temperature), loss_rows, ppos, (__nv_bfloat16*)p);
+  CMU_LAUNCH_CHECK();
+  mean_scale_kernel<<<1, 32, 0, st>>>(loss_rows, n, 1.f, loss);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+int cmu_moco_dq(const float* dq_neg, const float* k, const float* qh, const float* qnorm, const float* ppos, int n, int d,
+                float temperature, float* dq, void* stream) {
+  moco_dq_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(dq_neg, k, qh, qnorm, ppos, d, 1.f / ((float)n * temperature), dq);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+int cmu_queue_enqueue(const float* keys, int n, int d, int k, int ptr, void* queue_rows, float* queue_ref, void* stream) {
+  CMU_REQUIRE(ptr >= 0 && ptr < k, "queue_enqueue: bad pointer %d", ptr);
+  queue_enqueue_kernel<<<grid_for((size_t)n * d, 256, 4), 256, 0, (cudaStream_t)stream>>>(keys, n, d, k, ptr,
+                                                                                         (__nv_bfloat16*)queue_rows, queue_ref);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -138,6 +138,21 @@ int cmu_l2_normalize_rows(const float* x, float* y, int rows, int dim, void* str
 int cmu_infonce_fwd_bwd(const float* q, const float* z, int batch, int n_keys, int dim, int label_offset, float tau,
                         float ct_weight, float* loss_rows, float* loss, float* dq, void* stream);
 
+/* ---- a17  MoCo-v2 queue head (BASELINE configs[3]): Pretraining/MoCo/pl_bolts/models/self_supervised/moco/
+ * moco2_module.py:224-270 (logits = [q.k, q.Queue]/T, CE label 0), :160-175 (_dequeue_and_enqueue),
+ * moco_data_module.py:65 (spatial mean).  The K x N negative logits are produced by cmu_conv1x1_fprop (queue rows as
+ * pixels, normalised queries as weights) and dq_neg = P^T Queue by cmu_gemm_tn_bf16. */
+int cmu_spatial_mean(const void* x /* act (N,HW,C) */, float* out /* (N,C) */, int n, int hw, int c, void* stream);
+int cmu_spatial_mean_bwd(const float* dout, void* dx, int n, int hw, int c, void* stream);
+int cmu_moco_prep(const float* q, const float* k, int n, int d, void* qh16, float* qh, float* qnorm, float* lpos,
+                  void* stream);
+int cmu_moco_softmax(const void* lt /* bf16 [K][N] */, const float* lpos, int k, int n, float temperature,
+                     float* loss_rows, float* loss, float* ppos, void* p /* bf16 [K][N] or NULL */, void* stream);
+int cmu_moco_dq(const float* dq_neg, const float* k, const float* qh, const float* qnorm, const float* ppos, int n, int d,
+                float temperature, float* dq, void* stream);
+int cmu_queue_enqueue(const float* keys, int n, int d, int k, int ptr, void* queue_rows /* bf16 [K][D] */,
+                      float* queue_ref /* fp32 (D,K) reference layout or NULL */, void* stream);
+
 /* ---- a12/a16  EMA (cmunet.py:78-92) and AdamW (configs/cmunet_config.py:76-91) ---------------------------- */
 int cmu_ema_chunks(const long long* d_table /* [n][3] = dst, src, count */, int n_chunks, float momentum, void* stream);
 int cmu_adamw_chunks(const long long* d_table /* [n][6] = p, g, m, v, count, decay */, int n_chunks, float lr, float beta1,

@@ -434,6 +434,50 @@ def check_linear_tc(m=64, k=4096, n=1536, seed=20):
     return res
 
 
+def check_moco_head(n=64, d=1024, kneg=8192, seed=40):
+    """MoCo queue head (configs[3]) vs the oracle restatement: loss, dq, enqueue."""
+    from contrastive_masked_unet_b200.moco import MocoLossFn
+    from oracle import moco_oracle as MO
+    g = _gen(seed)
+    q = _randn((n, d), g).requires_grad_(True)
+    k = F.normalize(_randn((n, d), g), dim=1)
+    queue = F.normalize(_randn((d, kneg), g), dim=0)
+    rows = queue.t().contiguous().to(BF16)
+    qref = rows.float().t().contiguous()                       # the oracle sees the bf16-rounded queue
+    lr = MO.moco_loss(q, k, qref, 0.07)
+    lr.backward()
+    q2 = q.detach().clone().requires_grad_(True)
+    loss = MocoLossFn.apply(q2, k, rows, 0.07)
+    loss.backward()
+    # enqueue
+    keys = F.normalize(_randn((n, d), _gen(seed + 1)), dim=1)
+    qref2 = queue.clone()
+    ptr = MO.dequeue_and_enqueue(qref2, kneg - n, keys)
+    qdev = queue.clone()
+    lib.cmu_queue_enqueue(keys.data_ptr(), n, d, kneg, kneg - n, rows.data_ptr(), qdev.data_ptr(),
+                          torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    res = {'loss': abs(float(loss) - float(lr)) / float(lr), 'dq': rel_err(q2.grad, q.grad), 'dq_cos': cos(q2.grad, q.grad),
+           'enqueue_ref': float((qdev - qref2).abs().max()),
+           'enqueue_rows': float((rows[kneg - n:].float() - keys.to(BF16).float()).abs().max()), 'ptr': ptr}
+    assert res['loss'] < 2e-3 and res['dq_cos'] > 0.999 and res['dq'] < 5e-2, res
+    assert res['enqueue_ref'] == 0.0 and res['enqueue_rows'] == 0.0 and ptr == 0, res
+    return res
+
+
+def check_spatial_mean(n=3, h=8, w=6, c=1024, seed=41):
+    from contrastive_masked_unet_b200.moco import SpatialMeanFn
+    g = _gen(seed)
+    x = nhwc(_randn((n, c, h, w), g))
+    xr = nchw(x).requires_grad_(True)
+    out = SpatialMeanFn.apply(x.permute(0, 3, 1, 2).requires_grad_(True))
+    ref = torch.mean(xr, dim=[2, 3])
+    torch.cuda.synchronize()
+    res = {'mean': rel_err(out, ref.detach())}
+    assert res['mean'] < 1e-5, res
+    return res
+
+
 def check_bn1d(m=12, c=1536, seed=10):
     g = _gen(seed)
     x = _randn((m, c), g, 2.0)
@@ -553,6 +597,9 @@ CHECKS = {
     'gemm_tn_splitk': lambda: check_gemm_tn(50000, 64, 128, seed=22),
     'linear_tc': check_linear_tc,
     'linear_tc_128rows': lambda: check_linear_tc(128, 8192, 512, seed=23),
+    'moco_head_8k': check_moco_head,
+    'moco_head_64k': lambda: check_moco_head(64, 1024, 65536, seed=42),
+    'spatial_mean': check_spatial_mean,
     'bn1d': check_bn1d,
     'optim': check_optim,
 }

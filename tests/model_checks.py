@@ -238,6 +238,80 @@ def finetune_parity(B=4, S=256, seed=0, golden=None, grad_cos=0.999):
     return rep
 
 
+def moco_parity(N=64, S=64, K=4096, seed=7, steps=2):
+    """configs[3] (MoCo-v2 queue head): K2 training steps of the drop-in against oracle/moco_oracle.py (parity unpinned:
+    the reference module needs pytorch-lightning, see the oracle header)."""
+    from oracle import moco_oracle as MO
+    torch.manual_seed(seed)
+    m = C.Moco_v2(emb_dim=1024, num_negatives=K).to(DEV).train()
+    oq, ok = O.OracleEncoder().to(DEV).train(), O.OracleEncoder().to(DEV).train()
+    sd = {k: v.clone() for k, v in m.encoder_q.state_dict().items()}
+    oq.load_state_dict(sd)
+    ok.load_state_dict(sd)
+    queue = m.queue.clone()
+    # the drop-in keeps the negatives as bf16 rows; the oracle sees the same rounded values
+    queue_r = queue.to(torch.bfloat16).float()
+    ptr = 0
+    g = torch.Generator().manual_seed(seed)
+    rep = {'loss': [], 'fails': []}
+    for step in range(steps):
+        img_q = torch.rand(N, S, S, generator=g).to(DEV)
+        img_k = torch.rand(N, S, S, generator=g).to(DEV)
+        for p in m.encoder_q.parameters():
+            p.grad = None
+        loss = m.training_step(img_q, img_k)
+        loss.backward()
+        with torch.no_grad():                                          # moco2_module.py:153-158
+            for pq, pk in zip(oq.parameters(), ok.parameters()):
+                pk.mul_(0.999).add_(pq.detach(), alpha=0.001)
+        oq.zero_grad()
+        q = MO.moco_encoder_fwd(oq, img_q)
+        with torch.no_grad():
+            k = torch.nn.functional.normalize(MO.moco_encoder_fwd(ok, img_k), dim=1)
+        lr = MO.moco_loss(q, k, queue_r, 0.07)
+        lr.backward()
+        # what torch's own bf16 autocast of the oracle reaches (module docstring policy)
+        import copy
+        oa = copy.deepcopy(oq)
+        oa.zero_grad()
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            qa = MO.moco_encoder_fwd(oa, img_q)
+        MO.moco_loss(qa.float(), k, queue_r, 0.07).backward()
+        ac = {kn: cosine(p.grad, dict(oq.named_parameters())[kn].grad) for kn, p in oa.named_parameters()}
+        del oa
+        ptr = MO.dequeue_and_enqueue(queue, ptr, k)
+        queue_r[:, (ptr - N) % K:(ptr - N) % K + N] = k.T.to(torch.bfloat16).float()
+        torch.cuda.synchronize()
+        rep['loss'].append((float(loss), float(lr)))
+        if abs(float(loss) - float(lr)) > 1e-2 * abs(float(lr)):
+            rep['fails'].append(f'step {step}: loss {float(loss)} vs {float(lr)}')
+        ref = dict(oq.named_parameters())
+        worst = (2.0, None)
+        for kname, p in m.encoder_q.named_parameters():
+            if is_zero_grad_key(kname):
+                continue
+            c = cosine(p.grad, ref[kname].grad)
+            if c < worst[0]:
+                worst = (c, kname, ac[kname])
+            need = min(0.999, ac[kname] - (0.03 if ac[kname] >= 0.9 else 0.2))
+            if c < need:
+                rep['fails'].append(f'step {step} {kname}: grad cosine {c:.6f} < {need:.6f} (autocast {ac[kname]:.6f})')
+        rep.setdefault('worst_grad_cos', []).append(worst)
+    rep['queue_ptr'] = (int(m.queue_ptr), ptr)
+    # keys written by the drop-in come from a bf16 encoder: compare the enqueued columns loosely, untouched ones exactly
+    rep['queue_new_cos'] = cosine(m.queue[:, :ptr or K], queue[:, :ptr or K])
+    rep['queue_old_equal'] = bool(torch.equal(m.queue[:, ptr:], queue[:, ptr:])) if ptr else True
+    kd = dict(m.encoder_k.named_parameters())
+    rep['ema_max_abs'] = max(float((kd[kn] - p).abs().max()) for kn, p in ok.named_parameters())
+    if rep['queue_ptr'][0] != rep['queue_ptr'][1]:
+        rep['fails'].append(f'queue_ptr {rep["queue_ptr"]}')
+    if rep['queue_new_cos'] < 0.995 or not rep['queue_old_equal']:
+        rep['fails'].append(f'queue contents: cos {rep["queue_new_cos"]} old_equal {rep["queue_old_equal"]}')
+    if rep['ema_max_abs'] > 1e-6:
+        rep['fails'].append(f'EMA of the key encoder differs by {rep["ema_max_abs"]}')
+    return rep
+
+
 def golden_pretrain(S, B):
     for c in json.load(open(os.path.join(GOLD, 'pretrain.json')))['cases']:
         if c['S'] == S and c['B'] == B:

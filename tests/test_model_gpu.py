@@ -99,3 +99,11 @@ def test_finetune_S1024_config5_shape():
     from tests import model_checks as M
     rep = M.finetune_parity(1, 1024, seed=3)
     assert not rep['fails'], (rep['fails'][:8], {k: v for k, v in rep.items() if k != 'fails'})
+
+
+def test_moco_queue_head_two_steps_vs_oracle():
+    """BASELINE.json configs[3] scaled down (N=64, S=64, K=4096): loss, encoder_q grads, EMA of encoder_k, queue."""
+    _gpu()
+    from tests import model_checks as M
+    rep = M.moco_parity(64, 64, 4096)
+    assert not rep['fails'], rep

@@ -126,3 +126,20 @@ def test_module_head():
     (out['loss_ct'] + out['loss_rc']).backward()
     check_fp(pred.grad, c['d_pred'])
     check_fp(ps.grad, c['d_proj_s'], rtol=1e-3)
+
+
+def test_moco_oracle_self_consistency():
+    """oracle/moco_oracle.py is UNPINNED (reference MoCo needs pytorch-lightning); check its algebra against a manual
+    log-sum-exp and the enqueue pointer arithmetic of moco2_module.py:160-175."""
+    from oracle import moco_oracle as MO
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(8, 32, generator=g)
+    k = torch.nn.functional.normalize(torch.randn(8, 32, generator=g), dim=1)
+    queue = torch.nn.functional.normalize(torch.randn(32, 64, generator=g), dim=0)
+    qh = torch.nn.functional.normalize(q, dim=1)
+    logits = torch.cat([(qh * k).sum(1, keepdim=True), qh @ queue], 1) / 0.07
+    manual = (torch.logsumexp(logits, 1) - logits[:, 0]).mean()
+    assert abs(float(MO.moco_loss(q, k, queue, 0.07)) - float(manual)) < 1e-6
+    ptr = 56
+    ptr = MO.dequeue_and_enqueue(queue, ptr, k)
+    assert ptr == 0 and torch.equal(queue[:, 56:], k.T)
