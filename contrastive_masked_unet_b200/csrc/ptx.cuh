@@ -208,7 +208,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads issued by either CTA of a pair; data lands in the issuing CTA, the bytes are accounted on the mbarrier
 // at `mbar_cluster_addr` (the pair leader's barrier)
