@@ -53,6 +53,32 @@ __device__ __forceinline__ void column_sums(float (&v)[32], uint32_t lane) {
   bfly<1>(v, lane);
 }
 
+// BatchNorm statistics of one staged output slab (128 pixel rows x 64 channels, bf16, SWIZZLE_128B rows of 128 B):
+// warp q sums rows [32q, 32q+32), lane = channel pair, so one LDS.32 per row touches all 32 banks once and no
+// shuffles are needed.  The sums are taken over the bf16-ROUNDED outputs, i.e. exactly the values BatchNorm later
+// normalises.  valid_rows: bit r = pixel row 32q + r lies inside the image.
+__device__ __forceinline__ void slab_stats(const uint8_t* stg, uint32_t q, uint32_t lane, uint32_t valid_rows,
+                                           float* sum, float* sumsq) {
+  const uint8_t* base = stg + q * 32 * 128 + (lane & 3) * 4;
+  const uint32_t c16 = lane >> 2;
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    uint32_t w = *reinterpret_cast<const uint32_t*>(base + r * 128 + ((c16 ^ (uint32_t)(r & 7)) << 4));
+    if (!((valid_rows >> r) & 1u)) w = 0u;
+    const float x0 = __uint_as_float(w << 16);
+    const float x1 = __uint_as_float(w & 0xffff0000u);
+    a0 += x0;
+    a1 += x1;
+    b0 = fmaf(x0, x0, b0);
+    b1 = fmaf(x1, x1, b1);
+  }
+  red_shared_add(sum + 2 * lane, a0);
+  red_shared_add(sum + 2 * lane + 1, a1);
+  red_shared_add(sumsq + 2 * lane, b0);
+  red_shared_add(sumsq + 2 * lane + 1, b1);
+}
+
 
 // pair kernel (tc_conv2.cu): returns 0 on success; *used = 1 if the launch was taken by the pair kernel
 int run_k1_pair(K1Params& p, const void* wpk, int ktot, cudaStream_t stream, int* used_grid, int* used_bn);

@@ -183,6 +183,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
       const bool valid = (img < p.N) && (h0 + th < p.H) && (w0 + tw < p.W);
       const uint32_t acc = tile_it & 1;
       const uint32_t aph = (tile_it >> 1) & 1;
+      const uint32_t valid_rows = __ballot_sync(0xffffffffu, valid);
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
 #pragma unroll 1
@@ -223,22 +224,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
             const int chunk = (half * 4 + k4) ^ (row & 7);
             *reinterpret_cast<uint4*>(rowp + chunk * 16) = pk;
           }
-          if (p.stats != nullptr) {
-            float s1[32], s2[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float x = valid ? v[i] : 0.f;
-              s1[i] = x;
-              s2[i] = x * x;
-            }
-            column_sums(s1, lane);
-            column_sums(s2, lane);
-            red_shared_add(&s_stats[j * 32 + lane], s1[0]);
-            red_shared_add(&s_stats[BN + j * 32 + lane], s2[0]);
-          }
         }
         fence_proxy_async_smem();
         named_bar_sync(1, 128);
+        if (p.stats != nullptr)
+          slab_stats(stg, q, lane, valid_rows, &s_stats[slab * 64], &s_stats[BN + slab * 64]);
         if (store_thread) {
           const int nch = n0 + slab * 64;
           if (nch < p.oc0) tma_store_4d(&p.tmO0, stg, nch, w0, h0, img);

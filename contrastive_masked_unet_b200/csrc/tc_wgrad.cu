@@ -30,7 +30,9 @@ struct K2Params {
   int pc;              // channels of P
   int TW, TH, tiles_w, tiles_h, pix_tiles;
   int MT, NT, G, splits;
-  int m_atoms;         // 1 (M = 64 duplicated to 128) or 2
+  int m_atoms;         // 1 (M = 64 duplicated to 128, or two kernel rows stacked when `stack`) or 2
+  int stack;           // conv3x3 with 64 input channels: UMMA rows 0-63 = kernel row r, rows 64-127 = kernel row r+1
+                       // of the SAME smem patch (LBO = one patch row), so 3 kernel rows take 2 UMMA sets instead of 3
   int n_cols;          // 64 or 128
   int taps;            // accumulators per CTA: 3 (conv) or 1 (convT)
   float* ws;           // [splits][G*taps][QC][PC]
@@ -47,8 +49,9 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = (p.taps * p.n_cols <= 64) ? 64 : (p.taps * p.n_cols <= 128) ? 128
-                             : (p.taps * p.n_cols <= 256) ? 256 : 512;
+  const int acc_sets = p.stack ? 2 : p.taps;
+  const uint32_t tmem_cols = (acc_sets * p.n_cols <= 64) ? 64 : (acc_sets * p.n_cols <= 128) ? 128
+                             : (acc_sets * p.n_cols <= 256) ? 256 : 512;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kK2Stages; ++i) {
@@ -116,13 +119,14 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
   } else if (warp == 1) {
     // whole warp runs the loop (warp-uniform descriptors in uniform registers), one elected lane issues
     const uint32_t idesc = umma_idesc_bf16(128, p.n_cols, 1, 1);
-    const uint32_t a_lbo = (p.m_atoms == 2) ? kQAtom : 0;   // M = 64: both M atoms alias the same 64 channels
+    // M = 64: the second M atom is the same patch one kernel row further down (stack) or an alias of the first
+    const uint32_t a_lbo = (p.m_atoms == 2) ? kQAtom : p.stack ? (uint32_t)p.TW * 128 : 0;
     // MN-major SWIZZLE_128B: LBO = byte stride between 64-channel atoms, SBO = stride between 8-pixel K groups
     const uint64_t a_hi = umma_smem_desc(0, a_lbo, 1024);
     const uint64_t b_hi = umma_smem_desc(0, kPAtom, 1024);
-    const uint32_t tap_stride16 = (p.TW * 128) >> 4;
+    const uint32_t tap_stride16 = ((p.TW * 128) >> 4) * (p.stack ? 2 : 1);
     const uint32_t smem0 = smem_u32(smem);
-    const int taps = p.taps;
+    const int taps = acc_sets;
     uint32_t it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
       const uint32_t st = it % kK2Stages;
@@ -154,13 +158,16 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     const int QC = p.q0 + p.q1;
-    const bool row_ok = (p.m_atoms == 2 || row < 64) && (mt * 128 + (int)row < QC);
     const bool any = (t_end > t_begin);
-    for (int r = 0; r < p.taps; ++r) {
-      float* dst = p.ws + ((((size_t)split * p.G + g) * p.taps + r) * QC + (size_t)mt * 128 + row) * p.pc + (size_t)nt * p.n_cols;
+    for (int a = 0; a < acc_sets; ++a) {
+      // accumulator set a, TMEM lane `row` -> (kernel row r, input channel ch)
+      const int r = p.stack ? 2 * a + (int)(row >> 6) : a;
+      const int ch = (p.m_atoms == 2) ? mt * 128 + (int)row : (int)(row & 63);
+      const bool row_ok = (p.m_atoms == 2 || p.stack || row < 64) && r < p.taps && ch < QC;
+      float* dst = p.ws + ((((size_t)split * p.G + g) * p.taps + r) * QC + ch) * p.pc + (size_t)nt * p.n_cols;
       for (int j = 0; j < p.n_cols / 32; ++j) {
         uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + ((q * 32) << 16) + r * p.n_cols + j * 32, raw);
+        tmem_ld_32x32(tmem_base + ((q * 32) << 16) + a * p.n_cols + j * 32, raw);
         tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
@@ -312,6 +319,7 @@ static int run_k2(int mode, const void* q0, int qc0, const void* q1, int qc1, co
   p.TW = pl.TW; p.TH = pl.TH; p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.pix_tiles = pl.pix_tiles;
   p.MT = pl.MT; p.NT = pl.NT; p.G = pl.G; p.splits = pl.splits;
   p.m_atoms = pl.m_atoms; p.n_cols = pl.n_cols; p.taps = pl.taps;
+  p.stack = (mode == 0 && pl.m_atoms == 1 && debug_knob(8) == 0) ? 1 : 0;
   p.ws = ws;
   if (make_act_map4(&p.tmP, pten, N, H, W, pc, pl.TW, pl.TH)) return 1;
   if (mode == 0) {
