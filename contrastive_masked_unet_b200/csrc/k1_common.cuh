@@ -8,7 +8,7 @@ namespace cmu {
 
 enum { MODE_CONV3 = 0, MODE_PLAIN = 1, MODE_CONVT_FPROP = 2, MODE_CONVT_DGRAD = 3 };
 
-constexpr int kK1Threads = 192;
+constexpr int kK1Threads = 320;   // TMA warp, MMA warp, 2 groups of 4 epilogue warps (one group per TMEM accumulator)
 constexpr int kStagingBytes = 16384;  // one 128 x 64 bf16 output slab
 constexpr int kMaxStages = 8;
 constexpr int kSchedDepth = 4;
@@ -25,7 +25,8 @@ struct K1Params {
   int tiles_w, tiles_h, m_tiles, n_tiles;
   int kc;           // number of 64-wide K chunks per tap
   // shared-memory plan (host-computed): [n_stages x stage_bytes][stg_bufs x 16 KB staging][barriers][stats]
-  int a_bytes, b_bytes, b_off, stage_bytes, n_stages, stg_bufs;
+  int a_bytes, b_bytes, b_off, stage_bytes, n_stages, stg_bufs;   // stg_bufs: staging buffers PER epilogue group
+  int epi_groups;   // 1: warps 2-5 drain both accumulators; 2: warps 2-5 drain accumulator 0, warps 6-9 accumulator 1
   int w_resident;   // 1: this CTA's whole weight slab (all taps x K chunks of its n-tile) is loaded ONCE into shared
   int w_bytes;      //    memory and the pipeline streams activations only (small-weight layers)
   unsigned int* sched;  // [n_tiles] m-tile counters, zeroed before the launch (dynamic tile scheduler)
@@ -45,6 +46,16 @@ __device__ __forceinline__ void bfly(float (&v)[32], uint32_t lane) {
   }
 }
 // After the call, lane L holds in v[0] the sum over the 32 lanes of their v[L].
+// staging / epilogue-group plan: two groups with two 16 KB buffers each when the pipeline keeps >= 4 stages, then two
+// groups with one buffer, else the single-group plans.  (Short-K layers -- 64 channels, ConvTranspose, 1x1 -- are
+// bound by the epilogue's dependent-issue latency with one warp per scheduler; they have the shared memory to spare.)
+static inline void plan_epilogue(int avail, int stage_bytes, int force_single, int* epi_groups, int* stg_bufs) {
+  if (!force_single && (avail - 4 * kStagingBytes) / stage_bytes >= 4) { *epi_groups = 2; *stg_bufs = 2; }
+  else if (!force_single && (avail - 2 * kStagingBytes) / stage_bytes >= 5) { *epi_groups = 2; *stg_bufs = 1; }
+  else if ((avail - 2 * kStagingBytes) / stage_bytes >= 4) { *epi_groups = 1; *stg_bufs = 2; }
+  else { *epi_groups = 1; *stg_bufs = 1; }
+}
+
 __device__ __forceinline__ void column_sums(float (&v)[32], uint32_t lane) {
   bfly<16>(v, lane);
   bfly<8>(v, lane);
@@ -54,12 +65,12 @@ __device__ __forceinline__ void column_sums(float (&v)[32], uint32_t lane) {
 }
 
 // BatchNorm statistics of one staged output slab (128 pixel rows x 64 channels, bf16, SWIZZLE_128B rows of 128 B):
-// warp q sums rows [32q, 32q+32), lane = channel pair, so one LDS.32 per row touches all 32 banks once and no
+// each warp sums its own 32 staged rows (warp_stg), lane = channel pair, so one LDS.32 per row touches all 32 banks once and no
 // shuffles are needed.  The sums are taken over the bf16-ROUNDED outputs, i.e. exactly the values BatchNorm later
 // normalises.  valid_rows: bit r = pixel row 32q + r lies inside the image.
-__device__ __forceinline__ void slab_stats(const uint8_t* stg, uint32_t q, uint32_t lane, uint32_t valid_rows,
+__device__ __forceinline__ void slab_stats(const uint8_t* warp_stg, uint32_t lane, uint32_t valid_rows,
                                            float* sum, float* sumsq) {
-  const uint8_t* base = stg + q * 32 * 128 + (lane & 3) * 4;
+  const uint8_t* base = warp_stg + (lane & 3) * 4;
   const uint32_t c16 = lane >> 2;
   float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll

@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
   uint8_t* w_res = smem;                                   // [w_bytes] resident weights (w_resident mode)
   uint8_t* stage_base = smem + p.w_bytes;
   uint8_t* staging = stage_base + p.n_stages * p.stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + p.stg_bufs * kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + p.epi_groups * p.stg_bufs * kStagingBytes);
   uint64_t* full_bar = bars;                          // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;            // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;        // [2]
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
     }
     for (int i = 0; i < kSchedDepth; ++i) {
       mbar_init(&sfull_bar[i], 1);
-      mbar_init(&sempty_bar[i], 5);  // MMA lane + one lane of each of the 4 epilogue warps
+      mbar_init(&sempty_bar[i], 1 + 4 * p.epi_groups);  // MMA lane + one lane of each active epilogue warp
     }
     mbar_init(wfull_bar, 1);
     fence_mbar_init();
@@ -214,12 +214,16 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const uint32_t q = warp & 3;  // TMEM lane quadrant this warp may access
     const uint32_t row = q * 32 + lane;
-    const bool store_thread = (threadIdx.x == 64);
     const int th = row >> p.tw_shift;
     const int tw = row & (p.TW - 1);
+    const int wth0 = (int)(q * 32) >> p.tw_shift;   // first pixel row of this warp inside the tile
+    const int wtw0 = (int)(q * 32) & (p.TW - 1);
     const int stg_bufs = p.stg_bufs;
+    const uint32_t grp = (warp - 2) >> 2;             // epilogue group = the TMEM accumulator it drains
+    const bool two_groups = (p.epi_groups == 2);
+    uint8_t* const grp_staging = staging + grp * stg_bufs * kStagingBytes;
     uint32_t tile_it = 0, sit = 0, slab_it = 0;
-    while (true) {
+    while (grp < (uint32_t)p.epi_groups) {
       const uint32_t sslot = sit % kSchedDepth;
       mbar_wait(&sfull_bar[sslot], (sit / kSchedDepth) & 1);
       const int mt = sched_tile[sslot];
@@ -235,17 +239,19 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
       const uint32_t acc = tile_it & 1;
       const uint32_t aph = (tile_it >> 1) & 1;
       ++tile_it;
+      if (two_groups && acc != grp) continue;
       const uint32_t valid_rows = __ballot_sync(0xffffffffu, valid);
       mbar_wait(&tfull_bar[acc], aph);
       tc_fence_after();
 #pragma unroll 1
       for (int slab = 0; slab < BN / 64; ++slab, ++slab_it) {
-        uint8_t* stg = staging + (slab_it % stg_bufs) * kStagingBytes;
-        if (store_thread) {  // the store that last used this staging buffer has finished reading it
+        // warp-private staging (32 rows x 128 B) and warp-private TMA stores: no CTA-wide barrier in the tile loop
+        uint8_t* stg = grp_staging + (slab_it % stg_bufs) * kStagingBytes + q * 4096;
+        if (lane == 0) {  // the store that last used this staging buffer has finished reading it
           if (stg_bufs == 2) tma_store_wait_read1();
           else tma_store_wait_read0();
         }
-        named_bar_sync(1, 128);
+        __syncwarp();
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
           const int j = slab * 2 + half;
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
             }
           }
           // bf16 pack + swizzled staging store (16-byte chunk index XOR (row & 7): TMA SWIZZLE_128B pattern)
-          uint8_t* rowp = stg + row * 128;
+          uint8_t* rowp = stg + lane * 128;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             uint4 pk;
@@ -280,33 +286,32 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
             pk.y = pack_bf16(v[k4 * 8 + 2], v[k4 * 8 + 3]);
             pk.z = pack_bf16(v[k4 * 8 + 4], v[k4 * 8 + 5]);
             pk.w = pack_bf16(v[k4 * 8 + 6], v[k4 * 8 + 7]);
-            const int chunk = (half * 4 + k4) ^ (row & 7);
+            const int chunk = (half * 4 + k4) ^ (lane & 7);
             *reinterpret_cast<uint4*>(rowp + chunk * 16) = pk;
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (p.stats != nullptr)
-          slab_stats(stg, q, lane, valid_rows, &s_stats[slab * 64], &s_stats[BN + slab * 64]);
-        if (store_thread) {
+        __syncwarp();
+        if (lane == 0) {
           const int nch = n0 + slab * 64;
           if (p.mode == MODE_CONVT_FPROP) {
             const int rs = nch / p.oc0;
             const int co = nch - rs * p.oc0;
-            tma_store_5d(&p.tmO0, stg, (rs & 1) * p.oc0 + co, w0, rs >> 1, h0, img);
+            tma_store_5d(&p.tmO0, stg, (rs & 1) * p.oc0 + co, w0 + wtw0, rs >> 1, h0 + wth0, img);
           } else if (nch < p.oc0) {
-            tma_store_4d(&p.tmO0, stg, nch, w0, h0, img);
+            tma_store_4d(&p.tmO0, stg, nch, w0 + wtw0, h0 + wth0, img);
           } else {
-            tma_store_4d(&p.tmO1, stg, nch - p.oc0, w0, h0, img);
+            tma_store_4d(&p.tmO1, stg, nch - p.oc0, w0 + wtw0, h0 + wth0, img);
           }
           tma_store_commit();
         }
+        if (p.stats != nullptr) slab_stats(stg, lane, valid_rows, &s_stats[slab * 64], &s_stats[BN + slab * 64]);
       }
     }
-    if (store_thread) tma_store_wait_all0();
+    if (lane == 0) tma_store_wait_all0();
     if (p.stats != nullptr) {
-      named_bar_sync(1, 128);
-      for (int i = threadIdx.x - 64; i < 2 * BN; i += 128) p.stats[(size_t)blockIdx.x * 2 * BN + i] = s_stats[i];
+      named_bar_sync(1, 256);
+      for (int i = threadIdx.x - 64; i < 2 * BN; i += 256) p.stats[(size_t)blockIdx.x * 2 * BN + i] = s_stats[i];
     }
   }
   tc_fence_before();
@@ -446,13 +451,16 @@ static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int 
   } else {
     if (make_w_map(&p.tmB, wpk, 1, n_total, ktot, BN, 1)) return 1;
   }
+  // every epilogue warp stores its own 32 pixel rows: output box = 32 pixels (part of a tile row or 32/TW tile rows)
+  const int obox_w = p.TW < 32 ? p.TW : 32;
+  const int obox_h = 32 / obox_w;
   if (mode == MODE_CONVT_FPROP) {
-    if (make_up_map(&p.tmO0, out0, N, H, W, oc0, p.TW, p.TH)) return 1;
+    if (make_up_map(&p.tmO0, out0, N, H, W, oc0, obox_w, obox_h)) return 1;
     p.tmO1 = p.tmO0;
   } else {
-    if (make_act_map(&p.tmO0, out0, N, H, W, oc0, p.TW, p.TH)) return 1;
+    if (make_act_map(&p.tmO0, out0, N, H, W, oc0, obox_w, obox_h)) return 1;
     if (out1 != nullptr) {
-      if (make_act_map(&p.tmO1, out1, N, H, W, oc1, p.TW, p.TH)) return 1;
+      if (make_act_map(&p.tmO1, out1, N, H, W, oc1, obox_w, obox_h)) return 1;
     } else {
       p.tmO1 = p.tmO0;
     }
@@ -484,11 +492,11 @@ static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int 
     p.w_bytes = w_all;
     p.stage_bytes = p.b_off;
   }
-  p.stg_bufs = ((kSmemLimit - fixed - p.w_bytes - 2 * kStagingBytes) / p.stage_bytes >= 4) ? 2 : 1;
-  p.n_stages = (kSmemLimit - fixed - p.w_bytes - p.stg_bufs * kStagingBytes) / p.stage_bytes;
+  plan_epilogue(kSmemLimit - fixed - p.w_bytes, p.stage_bytes, debug_knob(9) == 1, &p.epi_groups, &p.stg_bufs);
+  p.n_stages = (kSmemLimit - fixed - p.w_bytes - p.epi_groups * p.stg_bufs * kStagingBytes) / p.stage_bytes;
   if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
   CMU_REQUIRE(p.n_stages >= 2, "k1: shared-memory plan failed (stage %d bytes)", p.stage_bytes);
-  const int smem_bytes = p.w_bytes + p.n_stages * p.stage_bytes + p.stg_bufs * kStagingBytes + fixed;
+  const int smem_bytes = p.w_bytes + p.n_stages * p.stage_bytes + p.epi_groups * p.stg_bufs * kStagingBytes + fixed;
   if (debug_knob(3) == 1) p.sched = nullptr;   // A/B switch: static tile schedule
   else if (next_sched_slot(&p.sched, p.n_tiles, stream)) return 1;
   int grid = num_sms();

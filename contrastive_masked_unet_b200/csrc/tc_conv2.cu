@@ -23,7 +23,7 @@
 
 namespace cmu {
 
-constexpr int kPairThreads = 192;
+constexpr int kPairThreads = kK1Threads;
 
 template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
@@ -32,7 +32,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
   uint8_t* staging = stage_base + p.n_stages * p.stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + p.stg_bufs * kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + p.epi_groups * p.stg_bufs * kStagingBytes);
   uint64_t* full_bar = bars;                    // [kMaxStages]  (used in the leader only)
   uint64_t* empty_bar = bars + kMaxStages;      // [kMaxStages]
   uint64_t* tfull_bar = bars + 2 * kMaxStages;  // [2]
@@ -169,12 +169,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
     // ------------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
     const uint32_t q = warp & 3;
     const uint32_t row = q * 32 + lane;
-    const bool store_thread = (threadIdx.x == 64);
     const int th = row >> p.tw_shift;
     const int tw = row & (p.TW - 1);
+    const int wth0 = (int)(q * 32) >> p.tw_shift;   // first pixel row of this warp inside the tile
+    const int wtw0 = (int)(q * 32) & (p.TW - 1);
     const int stg_bufs = p.stg_bufs;
+    const uint32_t grp = (warp - 2) >> 2;             // epilogue group = the TMEM accumulator it drains
+    const bool two_groups = (p.epi_groups == 2);
+    uint8_t* const grp_staging = staging + grp * stg_bufs * kStagingBytes;
     uint32_t tile_it = 0, slab_it = 0;
-    for (int sup = sup0; sup < n_super; sup += sup_stride, ++tile_it) {
+    for (int sup = sup0; sup < n_super && grp < (uint32_t)p.epi_groups; sup += sup_stride, ++tile_it) {
+      if (two_groups && (tile_it & 1) != grp) continue;
       const int mt = 2 * sup + (int)rank;
       const int img = mt / tiles_per_img;
       const int rem = mt - img * tiles_per_img;
@@ -188,12 +193,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
       tc_fence_after();
 #pragma unroll 1
       for (int slab = 0; slab < BN / 64; ++slab, ++slab_it) {
-        uint8_t* stg = staging + (slab_it % stg_bufs) * kStagingBytes;
-        if (store_thread) {
+        // warp-private staging (32 rows x 128 B) and warp-private TMA stores: no CTA-wide barrier in the tile loop
+        uint8_t* stg = grp_staging + (slab_it % stg_bufs) * kStagingBytes + q * 4096;
+        if (lane == 0) {
           if (stg_bufs == 2) tma_store_wait_read1();
           else tma_store_wait_read0();
         }
-        named_bar_sync(1, 128);
+        __syncwarp();
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
           const int j = slab * 2 + half;
@@ -213,7 +219,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + cb + i);
           }
-          uint8_t* rowp = stg + row * 128;
+          uint8_t* rowp = stg + lane * 128;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
             uint4 pk;
@@ -221,28 +227,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
             pk.y = pack_bf16(v[k4 * 8 + 2], v[k4 * 8 + 3]);
             pk.z = pack_bf16(v[k4 * 8 + 4], v[k4 * 8 + 5]);
             pk.w = pack_bf16(v[k4 * 8 + 6], v[k4 * 8 + 7]);
-            const int chunk = (half * 4 + k4) ^ (row & 7);
+            const int chunk = (half * 4 + k4) ^ (lane & 7);
             *reinterpret_cast<uint4*>(rowp + chunk * 16) = pk;
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (p.stats != nullptr)
-          slab_stats(stg, q, lane, valid_rows, &s_stats[slab * 64], &s_stats[BN + slab * 64]);
-        if (store_thread) {
+        __syncwarp();
+        if (lane == 0) {
           const int nch = n0 + slab * 64;
-          if (nch < p.oc0) tma_store_4d(&p.tmO0, stg, nch, w0, h0, img);
-          else tma_store_4d(&p.tmO1, stg, nch - p.oc0, w0, h0, img);
+          if (nch < p.oc0) tma_store_4d(&p.tmO0, stg, nch, w0 + wtw0, h0 + wth0, img);
+          else tma_store_4d(&p.tmO1, stg, nch - p.oc0, w0 + wtw0, h0 + wth0, img);
           tma_store_commit();
         }
+        if (p.stats != nullptr) slab_stats(stg, lane, valid_rows, &s_stats[slab * 64], &s_stats[BN + slab * 64]);
       }
     }
-    if (store_thread) tma_store_wait_all0();
+    if (lane == 0) tma_store_wait_all0();
     if (p.stats != nullptr) {
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       // partial row r with r % n_tiles == nt (the layout cmu_bn_finalize expects)
       const size_t srow = ((size_t)(cid / p.n_tiles) * 2 + rank) * p.n_tiles + nt;
-      for (int i = threadIdx.x - 64; i < 2 * BN; i += 128) p.stats[srow * 2 * BN + i] = s_stats[i];
+      for (int i = threadIdx.x - 64; i < 2 * BN; i += 256) p.stats[srow * 2 * BN + i] = s_stats[i];
     }
   }
   tc_fence_before();
@@ -291,11 +296,11 @@ int run_k1_pair(K1Params& p, const void* wpk, int ktot, cudaStream_t stream, int
   p.w_bytes = 0;
   p.sched = nullptr;
   const int fixed = 1024 + 320 + 2 * BN * 4 + 64;
-  p.stg_bufs = ((kSmemLimit - fixed - 2 * kStagingBytes) / p.stage_bytes >= 4) ? 2 : 1;
-  p.n_stages = (kSmemLimit - fixed - p.stg_bufs * kStagingBytes) / p.stage_bytes;
+  plan_epilogue(kSmemLimit - fixed, p.stage_bytes, debug_knob(9) == 1, &p.epi_groups, &p.stg_bufs);
+  p.n_stages = (kSmemLimit - fixed - p.epi_groups * p.stg_bufs * kStagingBytes) / p.stage_bytes;
   if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
   CMU_REQUIRE(p.n_stages >= 2, "k1 pair: shared-memory plan failed");
-  const int smem_bytes = p.n_stages * p.stage_bytes + p.stg_bufs * kStagingBytes + fixed;
+  const int smem_bytes = p.n_stages * p.stage_bytes + p.epi_groups * p.stg_bufs * kStagingBytes + fixed;
   int n_clusters = num_sms() / 2;
   const int n_super = (p.m_tiles + 1) / 2;
   if (n_clusters > n_super * p.n_tiles) n_clusters = n_super * p.n_tiles;

@@ -47,6 +47,7 @@ def main():
     ap.add_argument('--knobs', default='')
     ap.add_argument('--only', default='')
     ap.add_argument('--batch', type=int, default=64)
+    ap.add_argument('--reps', type=int, default=7)
     args = ap.parse_args()
     B = args.batch
     dev = 'cuda'
@@ -76,14 +77,26 @@ def main():
             flops = 2.0 * B * S * S * c0 * 4 * cout
             fns = {'fprop': lambda: ops.convT2x2_fprop(x0, wf, bias), 'dgrad': lambda: ops.convT2x2_dgrad(dy, wd),
                    'wgrad': lambda: ops.convT2x2_wgrad(x0, dy)}
-        for vname, knobs in variants:
-            for k, v in knobs:
-                lib.cmu_debug_set(k, v)
-            for op, fn in fns.items():
-                ms = time_fn(fn, flush)
+        # variants are interleaved (A B A B ...) so that clock / power drift hits all of them alike; median per variant
+        for op, fn in fns.items():
+            samples = {vname: [] for vname, _ in variants}
+            for vname, knobs in variants:       # warm-up of every variant
+                for k, v in knobs:
+                    lib.cmu_debug_set(k, v)
+                fn()
+                for k, v in knobs:
+                    lib.cmu_debug_set(k, 0)
+            for _ in range(args.reps):
+                for vname, knobs in variants:
+                    for k, v in knobs:
+                        lib.cmu_debug_set(k, v)
+                    samples[vname].append(time_fn(fn, flush, iters=1, warm=0))
+                    for k, v in knobs:
+                        lib.cmu_debug_set(k, 0)
+            for vname, _ in variants:
+                ts = sorted(samples[vname])
+                ms = ts[len(ts) // 2]
                 results[f'{name}.{op}[{vname}]'] = (ms, flops / ms / 1e9)
-            for k, v in knobs:
-                lib.cmu_debug_set(k, 0)
         line = f'{name:8s}'
         for op in fns:
             line += f' | {op}:'
