@@ -5,7 +5,7 @@ from ._lib import CmuError, lib  # noqa: F401
 from .modules import (CM_UNet, CMUNetPretrainHead, DoubleConv, DownBlock, MaskStream, MODELS, MUNetPretrainDecoder,  # noqa: F401
                       NonLinearNeck, UNet_encoder, UpBlock, build, cmunet_config, concat_all_gather,
                       try_register_mmengine)
-from .finetune import CrossEntropyLoss, DiceLoss, IoU, Loss, Metric, MultipliedLoss, SumOfLosses, UNet  # noqa: F401
+from .finetune import CrossEntropyLoss, DiceLoss, IoU, Loss, Metric, MultipliedLoss, SumOfLosses, UNet, soft_cldice  # noqa: F401
 
 from .moco import Moco_v2, MocoUNetEncoder  # noqa: F401
 

@@ -691,3 +691,147 @@ int cmu_queue_enqueue(const float* keys, int n, int d, int k, int ptr, void* que
 }
 
 }  // extern "C"
+
+// =========================================================================================== soft-clDice metric
+// Finetuning/metrics.py:401-492 (eval metric of Finetuning/train.py:464): soft skeletons of the thresholded prediction and
+// of the target by min/max-pool morphology (10 iterations), then the clDice ratio.  float64 planes like the reference's
+// float64 targets; HBM-bound, one 32x32 tile per CTA with a 3-pixel halo staged in shared memory.
+namespace cmu {
+
+__global__ void cldice_prep_kernel(const float* __restrict__ logits, const double* __restrict__ gt,
+                                   double* __restrict__ planes, size_t n, size_t hw) {
+  const size_t total = n * hw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t img = i / hw, p = i % hw;
+    planes[i] = (logits[(img * 2 + 1) * hw + p] > logits[(img * 2) * hw + p]) ? 1.0 : 0.0;   // softmax_1 > 0.5
+    planes[total + i] = gt[(img * 2 + 1) * hw + p];
+  }
+}
+
+constexpr int kSkT = 32;
+// one soft_skel step: e = kFirst ? in : erode(in); o = dilate(erode(e)); delta = relu(e - o);
+// skel = kFirst ? delta : skel + relu(delta - skel * delta); out = e
+template <bool kFirst>
+__global__ void __launch_bounds__(256) skel_step_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                        double* __restrict__ skel, int H, int W) {
+  __shared__ double s_in[kSkT + 6][kSkT + 7];
+  __shared__ double s_e[kSkT + 4][kSkT + 5];
+  __shared__ double s_ee[kSkT + 2][kSkT + 3];
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const size_t plane = (size_t)blockIdx.z * H * W;
+  const int y0 = blockIdx.y * kSkT, x0 = blockIdx.x * kSkT;
+  for (int i = threadIdx.x; i < (kSkT + 6) * (kSkT + 6); i += blockDim.x) {
+    const int ly = i / (kSkT + 6), lx = i % (kSkT + 6);
+    const int gy = y0 - 3 + ly, gx = x0 - 3 + lx;
+    s_in[ly][lx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? in[plane + (size_t)gy * W + gx] : inf;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (kSkT + 4) * (kSkT + 4); i += blockDim.x) {
+    const int ly = i / (kSkT + 4), lx = i % (kSkT + 4);
+    const int gy = y0 - 2 + ly, gx = x0 - 2 + lx;
+    double v = s_in[ly + 1][lx + 1];
+    if (!kFirst) v = fmin(fmin(fmin(v, s_in[ly][lx + 1]), s_in[ly + 2][lx + 1]), fmin(s_in[ly + 1][lx], s_in[ly + 1][lx + 2]));
+    s_e[ly][lx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? v : inf;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (kSkT + 2) * (kSkT + 2); i += blockDim.x) {
+    const int ly = i / (kSkT + 2), lx = i % (kSkT + 2);
+    const int gy = y0 - 1 + ly, gx = x0 - 1 + lx;
+    const double v = fmin(fmin(fmin(s_e[ly + 1][lx + 1], s_e[ly][lx + 1]), s_e[ly + 2][lx + 1]),
+                          fmin(s_e[ly + 1][lx], s_e[ly + 1][lx + 2]));
+    s_ee[ly][lx] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? v : -inf;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kSkT * kSkT; i += blockDim.x) {
+    const int ly = i / kSkT, lx = i % kSkT;
+    const int gy = y0 + ly, gx = x0 + lx;
+    if (gy >= H || gx >= W) continue;
+    double o = -inf;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) o = fmax(o, s_ee[ly + dy][lx + dx]);
+    const double e = s_e[ly + 2][lx + 2];
+    const double delta = fmax(e - o, 0.0);
+    const size_t idx = plane + (size_t)gy * W + gx;
+    if (kFirst) {
+      skel[idx] = delta;
+    } else {
+      const double sk = skel[idx];
+      skel[idx] = sk + fmax(delta - sk * delta, 0.0);
+      out[idx] = e;
+    }
+  }
+}
+
+// acc[0] = sum skel_pred * gt   acc[1] = sum skel_pred   acc[2] = sum skel_true * pred   acc[3] = sum skel_true
+__global__ void __launch_bounds__(256) cldice_sums_kernel(const double* __restrict__ planes, const double* __restrict__ skel,
+                                                          double* __restrict__ acc, size_t total) {
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const double sp = skel[i], st = skel[total + i];
+    a0 += sp * planes[total + i];
+    a1 += sp;
+    a2 += st * planes[i];
+    a3 += st;
+  }
+  __shared__ double sred[4][8];
+  a0 = warp_sum_d(a0); a1 = warp_sum_d(a1); a2 = warp_sum_d(a2); a3 = warp_sum_d(a3);
+  if ((threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    sred[0][w] = a0; sred[1][w] = a1; sred[2][w] = a2; sred[3][w] = a3;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double a = 0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a += sred[threadIdx.x][k];
+    atomicAdd(&acc[threadIdx.x], a);
+  }
+}
+__global__ void cldice_finish_kernel(const double* acc, double smooth, double* out) {
+  const double tprec = (acc[0] + smooth) / (acc[1] + smooth);
+  const double tsens = (acc[2] + smooth) / (acc[3] + smooth);
+  out[0] = 1.0 - 2.0 * (tprec * tsens) / (tprec + tsens);
+}
+
+}  // namespace cmu
+
+extern "C" {
+
+long long cmu_soft_cldice_workspace_bytes(int n, int h, int w) {
+  return (long long)(4 * 2 * (size_t)n * h * w + 8) * (long long)sizeof(double);
+}
+
+int cmu_soft_cldice(const float* logits, const double* gt, int n, int h, int w, int num_iter, double smooth, void* ws,
+                    long long ws_bytes, double* out, void* stream) {
+  using namespace cmu;
+  CMU_REQUIRE(n > 0 && h > 0 && w > 0 && num_iter >= 0, "soft_cldice: bad shape");
+  CMU_REQUIRE(ws != nullptr && ws_bytes >= cmu_soft_cldice_workspace_bytes(n, h, w), "soft_cldice: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t total = (size_t)n * h * w;          // per set (prediction planes, then target planes)
+  double* planes = (double*)ws;
+  double* buf_a = planes + 2 * total;
+  double* buf_b = buf_a + 2 * total;
+  double* skel = buf_b + 2 * total;
+  double* acc = skel + 2 * total;
+  CMU_CHECK_CUDA(cudaMemsetAsync(acc, 0, 4 * sizeof(double), st));
+  cldice_prep_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(logits, gt, planes, (size_t)n, (size_t)h * w);
+  CMU_LAUNCH_CHECK();
+  dim3 grid(ceil_div(w, kSkT), ceil_div(h, kSkT), 2 * n);
+  skel_step_kernel<true><<<grid, 256, 0, st>>>(planes, nullptr, skel, h, w);
+  CMU_LAUNCH_CHECK();
+  const double* cur = planes;
+  for (int j = 0; j < num_iter; ++j) {
+    double* nxt = (j & 1) ? buf_b : buf_a;
+    skel_step_kernel<false><<<grid, 256, 0, st>>>(cur, nxt, skel, h, w);
+    CMU_LAUNCH_CHECK();
+    cur = nxt;
+  }
+  cldice_sums_kernel<<<grid_for(total, 256, 8), 256, 0, st>>>(planes, skel, acc, total);
+  CMU_LAUNCH_CHECK();
+  cldice_finish_kernel<<<1, 1, 0, st>>>(acc, smooth, out);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -9,6 +9,7 @@ import torch.nn as nn
 
 from . import functional as Fn
 from . import ops
+from ._lib import lib
 from .modules import DoubleConv, DownBlock, UpBlock, register  # noqa: F401
 
 
@@ -178,6 +179,33 @@ class IoU(Metric):
     def forward(self, y_pr, y_gt):
         _check_cfg(self.activation, self.threshold, self.ignore_channels, y_pr)
         return _fused(y_pr, y_gt, iou_eps=self.eps)[1]
+
+
+class soft_cldice(Loss):
+    """FT/metrics.py:401-430: soft-clDice of the thresholded prediction against the float64 target (eval metric of
+    FT/train.py:464); 10 soft-skeleton iterations as the reference hard-codes (`iter_` is accepted and ignored there too)."""
+    __name__ = 'soft_clDice'
+
+    def __init__(self, iter_=3, smooth=1., exclude_background=False, threshold=0.5, activation=None, ignore_channels=None):
+        super().__init__()
+        if exclude_background:
+            raise NotImplementedError('exclude_background=True empties the single foreground channel (FT/metrics.py:421-423)')
+        self.iter, self.smooth, self.threshold = iter_, smooth, threshold
+        self.activation, self.ignore_channels = activation, ignore_channels
+
+    @torch.no_grad()
+    def forward(self, y_pred, y_true):
+        _check_cfg(self.activation, self.threshold, self.ignore_channels, y_pred)
+        ops._need_cuda(y_pred, y_true)
+        logits = y_pred.detach().contiguous().float()
+        gt = y_true.detach().contiguous().double()
+        n, _, h, w = logits.shape
+        nbytes = lib.cmu_soft_cldice_workspace_bytes(n, h, w)
+        ws = torch.empty(nbytes // 8, dtype=torch.float64, device=logits.device)
+        out = torch.empty(1, dtype=torch.float64, device=logits.device)
+        lib.cmu_soft_cldice(logits.data_ptr(), gt.data_ptr(), n, h, w, 10, float(self.smooth), ws.data_ptr(), nbytes,
+                            out.data_ptr(), ops._stream())
+        return out.reshape(())
 
 
 class CrossEntropyLoss(Loss):

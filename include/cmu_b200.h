@@ -162,6 +162,12 @@ int cmu_adamw_chunks(const long long* d_table /* [n][6] = p, g, m, v, count, dec
 int cmu_seg_losses(const float* logits, const double* gt, double* acc /* double[4] */, double* out /* dice, iou, ce */,
                    float* dlogits /* or NULL */, const float* gscale, int n, int h, int w, double dice_eps, double beta,
                    double iou_eps, void* stream);
+/* soft-clDice evaluation metric (FT/metrics.py:401-492, used by FT/train.py:464): prediction = [logit1 > logit0], target =
+ * gt[:,1] (float64), soft skeletons by min/max-pool morphology with num_iter iterations (the reference fixes 10);
+ * out[0] = 1 - 2 tprec tsens / (tprec + tsens), float64. */
+long long cmu_soft_cldice_workspace_bytes(int n, int h, int w);
+int cmu_soft_cldice(const float* logits, const double* gt, int n, int h, int w, int num_iter, double smooth, void* ws,
+                    long long ws_bytes, double* out, void* stream);
 
 #ifdef __cplusplus
 }

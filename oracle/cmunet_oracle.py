@@ -316,6 +316,44 @@ def ce_prob_loss(logits, gt):
     return F.cross_entropy(logits, gt)
 
 
+def soft_skel(img, num_iter=10):
+    """FT/metrics.py:447-492 (SoftSkeletonize, 2-D case): min/max-pool morphology, padding ignored by the pools."""
+    def erode(t):
+        return torch.min(-F.max_pool2d(-t, (3, 1), (1, 1), (1, 0)), -F.max_pool2d(-t, (1, 3), (1, 1), (0, 1)))
+
+    def opened(t):
+        return F.max_pool2d(erode(t), (3, 3), (1, 1), (1, 1))
+
+    skel = F.relu(img - opened(img))
+    for _ in range(num_iter):
+        img = erode(img)
+        delta = F.relu(img - opened(img))
+        skel = skel + F.relu(delta - skel * delta)
+    return skel
+
+
+def cldice_loss(logits, gt, smooth=1.0, threshold=0.5, ignore_channels=(0,), num_iter=10):
+    """FT/metrics.py:401-430 (soft_cldice with activation='softmax'): thresholded prediction vs float64 target."""
+    pr = (torch.softmax(logits, dim=1) > threshold).type(logits.dtype)
+    keep = [c for c in range(pr.shape[1]) if c not in ignore_channels]
+    pr, gt = pr[:, keep], gt[:, keep]
+    skel_pred, skel_true = soft_skel(pr, num_iter), soft_skel(gt, num_iter)
+    tprec = (torch.sum(skel_pred * gt) + smooth) / (torch.sum(skel_pred) + smooth)
+    tsens = (torch.sum(skel_true * pr) + smooth) / (torch.sum(skel_true) + smooth)
+    return 1. - 2.0 * (tprec * tsens) / (tprec + tsens)
+
+
+def cldice_inputs(n, h, w, seed):
+    """Deterministic vessel-like test inputs: logits (n,2,h,w) fp32 and a one-hot float64 target from smoothed noise."""
+    g = torch.Generator().manual_seed(seed)
+    a = F.avg_pool2d(torch.rand(n, 1, h + 8, w + 8, generator=g), 9, 1)           # (n,1,h,w) smooth field
+    b = F.avg_pool2d(torch.rand(n, 1, h + 8, w + 8, generator=g), 9, 1)
+    y1 = ((a - 0.5).abs() < 0.012)                                                # thin iso-contours
+    logits = torch.cat([torch.zeros(n, 1, h, w), 40.0 * (0.02 - (a - 0.5 + 0.05 * (b - 0.5)).abs())], 1)
+    logits = logits + 0.05 * torch.randn(n, 2, h, w, generator=g)
+    return logits.float(), torch.cat([~y1, y1], 1).double()
+
+
 # ----------------------------------------------------------------------------------------------
 # summaries used by the golden fixtures (small, deterministic fingerprints of big tensors)
 # ----------------------------------------------------------------------------------------------

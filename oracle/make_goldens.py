@@ -163,6 +163,23 @@ def gold_finetune(seed=0):
     return rec
 
 
+def gold_cldice():
+    """FT/metrics.py:401-430 soft_cldice (the eval metric of FT/train.py:464) on deterministic synthetic inputs."""
+    from oracle.cmunet_oracle import cldice_inputs
+    _, metrics = ref_loader.import_finetune()
+    m = metrics.soft_cldice(threshold=0.5, activation='softmax', ignore_channels=[0])
+    cases = []
+    for n, h, w, seed in ((2, 64, 64, 3), (3, 48, 80, 4), (1, 33, 21, 5)):
+        logits, gt = cldice_inputs(n, h, w, seed)
+        val = m(logits, gt)
+        pr = (torch.softmax(logits, 1) > 0.5).float()[:, 1:]
+        cases.append({'n': n, 'h': h, 'w': w, 'seed': seed, 'name': m.__name__, 'cldice': float(val), 'dtype': str(val.dtype),
+                      'pred_pixels': float(pr.sum()), 'gt_pixels': float(gt[:, 1].sum()),
+                      'skel_pred_sum': float(m.soft_skeletonize(pr).sum()),
+                      'skel_true_sum': float(m.soft_skeletonize(gt[:, 1:]).sum())})
+    return cases
+
+
 def main():
     if not ref_loader.reference_available():
         raise SystemExit('reference tree not found: goldens can only be minted in the build container')
@@ -176,6 +193,9 @@ def main():
     if 'modules' in which:
         json.dump({'meta': meta, 'cases': gold_modules()}, open(os.path.join(GOLD, 'modules.json'), 'w'), indent=1)
         print('modules done')
+    if 'cldice' in which:
+        json.dump({'meta': meta, 'cases': gold_cldice()}, open(os.path.join(GOLD, 'cldice.json'), 'w'), indent=1)
+        print('cldice done')
     if 'finetune' in which:
         json.dump({'meta': meta, 'case': gold_finetune()}, open(os.path.join(GOLD, 'finetune.json'), 'w'), indent=1)
         print('finetune done')

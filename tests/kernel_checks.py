@@ -483,6 +483,32 @@ def check_spatial_mean(n=3, h=8, w=6, c=1024, seed=41):
     return res
 
 
+def check_cldice():
+    """soft-clDice metric vs the oracle and the golden values minted from the reference (bit-exact on binary masks)."""
+    import json
+    import os
+    import contrastive_masked_unet_b200 as C
+    from oracle import cmunet_oracle as O
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'cldice.json')))['cases']
+    m = C.soft_cldice(threshold=0.5, activation='softmax', ignore_channels=[0])
+    res = {'name': m.__name__}
+    for c in gold:
+        logits, gt = O.cldice_inputs(c['n'], c['h'], c['w'], c['seed'])
+        v = m(logits.cuda(), gt.cuda())
+        ref = O.cldice_loss(logits, gt)
+        res[f"{c['n']}x{c['h']}x{c['w']}"] = (float(v), float(ref), c['cldice'])
+        assert v.dtype == torch.float64 and abs(float(v) - c['cldice']) < 1e-12 and abs(float(v) - float(ref)) < 1e-12, res
+    # soft (non-binary) target: float64 morphology must still agree
+    g = _gen(77)
+    logits = torch.randn(2, 2, 70, 45, generator=g).cuda()
+    y1 = torch.rand(2, 1, 70, 45, generator=g).double().cuda()
+    gt = torch.cat([1 - y1, y1], 1)
+    v, ref = m(logits, gt), O.cldice_loss(logits, gt)
+    res['soft_target'] = (float(v), float(ref))
+    assert abs(float(v) - float(ref)) < 1e-9, res
+    return res
+
+
 def check_bn1d(m=12, c=1536, seed=10):
     g = _gen(seed)
     x = _randn((m, c), g, 2.0)
@@ -605,6 +631,7 @@ CHECKS = {
     'moco_head_8k': check_moco_head,
     'moco_head_64k': lambda: check_moco_head(64, 1024, 65536, seed=42),
     'spatial_mean': check_spatial_mean,
+    'cldice': check_cldice,
     'bn1d': check_bn1d,
     'optim': check_optim,
 }

@@ -143,3 +143,18 @@ def test_moco_oracle_self_consistency():
     ptr = 56
     ptr = MO.dequeue_and_enqueue(queue, ptr, k)
     assert ptr == 0 and torch.equal(queue[:, 56:], k.T)
+
+
+def test_cldice_oracle_matches_reference_golden():
+    """oracle.cldice_loss (FT/metrics.py:401-492 restated) against values minted from the reference's soft_cldice."""
+    import json, os
+    from oracle import cmunet_oracle as O
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'cldice.json')))['cases']
+    for c in gold:
+        logits, gt = O.cldice_inputs(c['n'], c['h'], c['w'], c['seed'])
+        pr = (torch.softmax(logits, 1) > 0.5).float()[:, 1:]
+        assert float(pr.sum()) == c['pred_pixels'] and float(gt[:, 1].sum()) == c['gt_pixels']
+        assert float(O.soft_skel(pr).sum()) == c['skel_pred_sum']
+        assert float(O.soft_skel(gt[:, 1:]).sum()) == c['skel_true_sum']
+        v = O.cldice_loss(logits, gt)
+        assert str(v.dtype) == c['dtype'] and abs(float(v) - c['cldice']) < 1e-12
