@@ -30,6 +30,9 @@ def algorithmic_flops_per_image(S):
     return FLOPS_PER_IMAGE_512 * (S / 512.0) ** 2
 
 
+K1_DRAM_BYTES_PER_LAUNCH = 1.915e9   # measured, see roofline.traffic_note
+
+
 def measured_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -253,11 +256,12 @@ def run_ours(args):
         achieved = (k1_fl / (k1_ms / 1e3)) / 1e12 if k1_ms > 0 else 0.0
         roofline = {'bound': 'tensor', 'kernel': 'k1_kernel (tcgen05 implicit-GEMM conv3x3 fprop+dgrad)',
                     'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                    'frac': achieved / peaks['bf16_tflops'], 'traffic': None, 'peak_source': peaks['source'],
-                    'traffic_note': 'achieved aggregates ~60 K1 launches of different layers per step, so there is no '
-                                    'single per-launch byte count; ncu --set full of one representative launch '
-                                    '(enc3.conv2 fprop, B=64): dram read+write 1.030 GB vs 1.074 GB algorithmic '
-                                    '(profiles/r1_k1pair_ncu_full.md)',
+                    'frac': achieved / peaks['bf16_tflops'],
+                    'traffic': K1_DRAM_BYTES_PER_LAUNCH if (B, S) == (64, 512) else None, 'peak_source': peaks['source'],
+                    'traffic_note': 'bytes per K1 launch, dram__bytes_read.sum + dram__bytes_write.sum averaged over the 60 '
+                                    'k1_pair launches of one step of this command (ncu, profiles/r1_k2_dram_traffic.md, '
+                                    'profiles/r1_step_dram_traffic.json); algorithmic bytes (every activation tile loaded '
+                                    'once, every output stored once) are the same 1.9 GB: no wasted re-reads',
                     'launches': k1_n, 'avg_launch_ms': k1_ms / max(1, k1_n), 'share_of_step': k1_ms / ms_prof,
                     'measured': f'CUDA events around every launch in a second pass of {args.steps} steps on ONE stream '
                                 f'({ms_prof / args.steps:.1f} ms/step; the 3-stream production schedule of the timed region '

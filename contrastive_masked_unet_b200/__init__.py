@@ -10,3 +10,15 @@ from .finetune import CrossEntropyLoss, DiceLoss, IoU, Loss, Metric, MultipliedL
 from .moco import Moco_v2, MocoUNetEncoder  # noqa: F401
 
 __version__ = '0.1.0'
+
+
+def _apply_env_knobs():
+    """CMU_DEBUG_KNOBS="10=1,9=1": A/B switches of include/cmu_b200.h:cmu_debug_set for whole-step experiments."""
+    import os
+    spec = os.environ.get('CMU_DEBUG_KNOBS', '')
+    for kv in filter(None, spec.split(',')):
+        k, v = kv.split('=')
+        lib.cmu_debug_set(int(k), int(v))
+
+
+_apply_env_knobs()

@@ -20,6 +20,7 @@ constexpr int kQAtom = 20480;   // haloed patch atom (max (TH+2)*TW*128)
 constexpr int kPAtom = 16384;   // plain 128-pixel atom
 constexpr int kK2Stage = 2 * kQAtom + 2 * kPAtom;
 constexpr int kK2Stages = 3;
+constexpr int kPace = 4;
 constexpr int kK2Smem = kK2Stages * kK2Stage + 1024 + 512;
 
 struct K2Params {
@@ -31,6 +32,8 @@ struct K2Params {
   int TW, TH, tiles_w, tiles_h, pix_tiles;
   int MT, NT, G, splits;
   int m_atoms;         // 1 (M = 64 duplicated to 128, or two kernel rows stacked when `stack`) or 2
+  int paced;           // launched as clusters of G CTAs (the G kernel-column / tap groups of one pixel range): their TMA
+                       // producers meet every kPace pixel tiles so the shared Q / P tiles are still in L2 for the others
   int stack;           // conv3x3 with 64 input channels: UMMA rows 0-63 = kernel row r, rows 64-127 = kernel row r+1
                        // of the SAME smem patch (LBO = one patch row), so 3 kernel rows take 2 UMMA sets instead of 3
   int n_cols;          // 64 or 128
@@ -45,7 +48,8 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kK2Stages;
   uint64_t* tfull_bar = bars + 2 * kK2Stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  uint64_t* pace_bar = tfull_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pace_bar + 1);
 
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t lane = threadIdx.x & 31;
@@ -59,6 +63,7 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(tfull_bar, 1);
+    mbar_init(pace_bar, p.G);
     fence_mbar_init();
     tma_prefetch_desc(&p.tmP);
     tma_prefetch_desc(&p.tmQ0);
@@ -69,13 +74,14 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (p.paced) cluster_sync_all();   // every CTA's pace barrier is initialised before a peer arrives on it
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // CTA -> (m tile, n tile, tap group, split)
+  // CTA -> (m tile, n tile, split, tap group); the tap group is the rank inside the cluster when paced
   int b = blockIdx.x;
-  const int split = b % p.splits; b /= p.splits;
   const int g = b % p.G;          b /= p.G;
+  const int split = b % p.splits; b /= p.splits;
   const int nt = b % p.NT;
   const int mt = b / p.NT;
   const int t_begin = (int)(((long long)p.pix_tiles * split) / p.splits);
@@ -87,7 +93,7 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t tx = p.m_atoms * q_atom_bytes + n_atoms * kPAtom;
-      uint32_t it = 0;
+      uint32_t it = 0, pace_phase = 0;
       for (int t = t_begin; t < t_end; ++t, ++it) {
         const int img = t / tiles_per_img;
         const int rem = t - img * tiles_per_img;
@@ -113,6 +119,14 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
         }
         for (int a = 0; a < n_atoms; ++a)
           tma_load_4d(sP + a * kPAtom, &p.tmP, &full_bar[st], nt * p.n_cols + a * 64, w0, h0, img);
+        if (p.paced && ((it % kPace) == kPace - 1 || t == t_end - 1)) {
+          // all G CTAs of the cluster walk the same pixel tiles: tell every one of them (and myself) that I am here,
+          // then wait until all of them are
+          const uint32_t pb = smem_u32(pace_bar);
+          for (int c = 0; c < p.G; ++c) mbar_arrive_cluster(mapa_u32(pb, (uint32_t)c));
+          mbar_wait(pace_bar, pace_phase);
+          pace_phase ^= 1u;
+        }
       }
     }
     __syncwarp();
@@ -185,6 +199,7 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (p.paced) cluster_sync_all();   // no CTA leaves while a peer may still arrive on its pace barrier
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -245,6 +260,9 @@ static int make_up_map5(CUtensorMap* m, const void* base, int N, int H, int W, i
   return encode_tmap_bf16(m, base, 5, dims, str, box);
 }
 
+// CTAs that can be co-resident when the kernel is launched as clusters of `g` (clusters must fit inside a GPC)
+static int k2_cluster_slots(int g);
+
 struct K2Plan {
   int TW, TH, tiles_w, tiles_h, pix_tiles, MT, NT, G, splits, m_atoms, n_cols, taps;
 };
@@ -276,7 +294,7 @@ static void plan_k2(int mode, int N, int H, int W, int qc, int pc, K2Plan* pl) {
   // cost (TMEM alloc, pipeline fill, fp32 partial-block epilogue) being worth ~10 pixel-tile stages.  This fills the
   // machine for small layers and repairs the 1.3-wave quantisation of the big ones (192 CTAs on 148 SMs).
   const int base = pl->MT * pl->NT * pl->G;
-  const int sms = num_sms();
+  const int sms = (pl->G > 1 && debug_knob(10) == 1) ? k2_cluster_slots(pl->G) : num_sms();
   const long long per_split_bytes = (long long)pl->G * pl->taps * qc * pc * 4;
   int splits = 1;
   double best = 1e300;
@@ -291,6 +309,32 @@ static void plan_k2(int mode, int N, int H, int W, int qc, int pc, K2Plan* pl) {
     }
   }
   pl->splits = splits;
+}
+
+static int k2_cluster_slots(int g) {
+  static int cache[8] = {0};
+  if (g < 1 || g > 7) return num_sms();
+  if (cache[g] == 0) {
+    cudaFuncSetAttribute(k2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kK2Smem);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(g * num_sms()), 1, 1);
+    cfg.blockDim = dim3(kK2Threads, 1, 1);
+    cfg.dynamicSmemBytes = kK2Smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)g;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k2_kernel, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = num_sms() / g;
+    }
+    cache[g] = n * g;
+  }
+  return cache[g];
 }
 
 int simt_wgrad(int mode, const void* x0, int c0, const void* x1, int c1, const void* dy, int cout, int N, int H, int W,
@@ -342,7 +386,24 @@ static int run_k2(int mode, const void* q0, int qc0, const void* q1, int qc1, co
     attr_set = true;
   }
   const int grid = pl.MT * pl.NT * pl.G * pl.splits;
-  k2_kernel<<<grid, kK2Threads, kK2Smem, stream>>>(p);
+  p.paced = (pl.G > 1 && debug_knob(10) == 1) ? 1 : 0;   // A/B: see profiles/r1_k2_dram_traffic.md
+  if (p.paced) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(kK2Threads, 1, 1);
+    cfg.dynamicSmemBytes = kK2Smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)pl.G;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CMU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k2_kernel, p));
+  } else {
+    k2_kernel<<<grid, kK2Threads, kK2Smem, stream>>>(p);
+  }
   CMU_LAUNCH_CHECK();
   const int total = pl.G * pl.taps * qc * pc;
   if (mode == 0)
