@@ -61,6 +61,25 @@ def main():
            'grad_cos_all': num / (den_a ** 0.5 * den_b ** 0.5), 'grads_equal_across_ranks': bool(torch.equal(flat, ref)),
            'bn_rm_err': float((m.projector.bn0.running_mean - o.projector.bn0.running_mean).abs().max() /
                               o.projector.bn0.running_mean.abs().max())}
+    # MoCo queue head across ranks (moco2_module.py:160-175 + :404-413): keys of ALL ranks enter every rank's queue in rank
+    # order, so the queues stay identical; the first 2N columns are the two ranks' normalised keys.
+    torch.manual_seed(7)
+    N, K = 64, 1024
+    moco = C.Moco_v2(emb_dim=1024, num_negatives=K).to(dev).train()
+    gq = torch.Generator().manual_seed(100 + rank)
+    iq, ik = torch.rand(N, 64, 64, generator=gq).to(dev), torch.rand(N, 64, 64, generator=gq).to(dev)
+    loss = moco.training_step(iq, ik)
+    loss.backward()
+    with torch.no_grad():
+        k_local = torch.nn.functional.normalize(moco.encoder_k(ik).float(), dim=1)
+    qsum = moco.queue[:, :world * N].double().sum().reshape(1)
+    qs = [torch.zeros_like(qsum) for _ in range(world)]
+    dist.all_gather(qs, qsum)
+    torch.cuda.synchronize()
+    res['moco'] = {'loss': float(loss), 'ptr': int(moco.queue_ptr),
+                   'queues_equal': bool(all(torch.equal(q, qs[0]) for q in qs)),
+                   'own_keys_err': float((moco.queue[:, rank * N:(rank + 1) * N].t() - k_local).abs().max()),
+                   'rows_match_queue': float((moco._rows[:world * N].float() - moco.queue[:, :world * N].t()).abs().max())}
     out = [None] * world
     dist.all_gather_object(out, res)
     if rank == 0:

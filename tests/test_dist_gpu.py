@@ -28,3 +28,7 @@ def test_two_rank_ddp_matches_oracle():
         assert rr['grads_equal_across_ranks'], rr
         assert rr['bn_rm_err'] < 5e-2, rr
     assert res[0]['loss_ct'][1] != res[1]['loss_ct'][1]
+    for rr in res:
+        mo = rr['moco']
+        assert mo['ptr'] == 128 and mo['queues_equal'] and mo['loss'] > 0, rr
+        assert mo['own_keys_err'] < 2e-2 and mo['rows_match_queue'] < 1e-2, rr   # bf16 encoder / bf16 row copy
