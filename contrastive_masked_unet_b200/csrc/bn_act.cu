@@ -2,6 +2,7 @@
 // the patch-mask multiply), BatchNorm statistics finalisation, BN-apply + ReLU (+ 2x2 max-pool), and the
 // BatchNorm/ReLU/max-pool backward passes.  All activations are NHWC bf16; every thread moves 16-byte vectors
 // (8 channels) so that warps read/write whole 128-byte lines.
+#include <algorithm>
 #include "common.cuh"
 #include "../../include/cmu_b200.h"
 
@@ -399,8 +400,18 @@ __global__ void __launch_bounds__(256) bn_relu_pool_kernel(const __nv_bfloat16* 
 // dz = g * [z > 0],  z = y*scale + shift,  xhat = (y - mean) * rstd
 // pass 1: per-channel sum(dz), sum(dz * xhat)  -> partial[block][2][C]
 // pass 2: dy = scale * (dz - sum_dz/n - xhat * sum_dzx/n)
+template <typename K>
+static int resident_blocks(K kernel, int threads, size_t smem) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) {
+    cudaGetLastError();
+    n = 1;
+  }
+  return n;
+}
+
 template <bool kPool, bool kApply>
-__global__ void __launch_bounds__(256) bn_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ dpool,
+__global__ void __launch_bounds__(256, kPool ? 2 : 3) bn_bwd_kernel(const __nv_bfloat16* __restrict__ da, const __nv_bfloat16* __restrict__ dpool,
                                                      const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
                                                      const float* __restrict__ shift, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const float* __restrict__ sums,
@@ -445,38 +456,43 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const __nv_bfloat16* __rest
         const size_t nb = u / ((size_t)Wq * Hq);
         float gp[8];
         unpack8(reinterpret_cast<const uint4*>(dpool)[u * cgs + cg], gp);
-        float yv[4][8], z[4][8];
+        float yv[4][8];
         size_t pixs[4];
+        uint4 rg[4];
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
           pixs[d] = (nb * H + (hp * 2 + (d >> 1))) * W + (wp * 2 + (d & 1));
-          unpack8(reinterpret_cast<const uint4*>(y)[pixs[d] * cgs + cg], yv[d]);
+          unpack8(__ldcs(reinterpret_cast<const uint4*>(y) + pixs[d] * cgs + cg), yv[d]);
+          rg[d] = (da != nullptr) ? __ldcs(reinterpret_cast<const uint4*>(da) + pixs[d] * cgs + cg) : make_uint4(0, 0, 0, 0);
+        }
+        // per channel: which window element the forward pooled (first maximum in row-major order of the bf16-rounded
+        // activations, exactly what bn_relu_pool compared) and which elements passed the ReLU
+        int win[8];
+        bool pos[4][8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            // compare the bf16-rounded activations, exactly what the forward pooled
-            z[d][k] = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(yv[d][k], sc[k], sh[k]), 0.f)));
+        for (int k = 0; k < 8; ++k) {
+          float zb[4];
+#pragma unroll
+          for (int d = 0; d < 4; ++d)
+            zb[d] = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(yv[d][k], sc[k], sh[k]), 0.f)));
+          float m = zb[0];
+          int w = 0;
+#pragma unroll
+          for (int d = 1; d < 4; ++d) {
+            if (zb[d] > m) { m = zb[d]; w = d; }
           }
+          win[k] = w;
+#pragma unroll
+          for (int d = 0; d < 4; ++d) pos[d][k] = zb[d] > 0.f;
         }
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-          float g[8];
-          if (da != nullptr) unpack8(reinterpret_cast<const uint4*>(da)[pixs[d] * cgs + cg], g);
-          else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) g[k] = 0.f;
-          }
-          float o[8];
+          float g[8], o[8];
+          unpack8(rg[d], g);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            // first maximum in row-major window order
-            bool is_max = true;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (e < d) is_max = is_max && (z[d][k] > z[e][k]);
-              if (e > d) is_max = is_max && (z[d][k] >= z[e][k]);
-            }
-            const float gg = g[k] + (is_max ? gp[k] : 0.f);
-            const float dz = (z[d][k] > 0.f) ? gg : 0.f;
+            const float gg = g[k] + (win[k] == d ? gp[k] : 0.f);
+            const float dz = pos[d][k] ? gg : 0.f;
             const float xh = (yv[d][k] - mu[k]) * rs[k];
             if (kApply) o[k] = sc[k] * (dz - k1[k] - xh * k2[k]);
             else { a1[k] += dz; a2[k] += dz * xh; }
@@ -540,7 +556,21 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 #pragma unroll
   for (int k = 0; k < 8; ++k) a[k] = 0.f;
   if (slot < slots) {
-    for (size_t r = (size_t)blockIdx.x * slots + slot; r < rows; r += (size_t)gridDim.x * slots) {
+    const size_t stride = (size_t)gridDim.x * slots;
+    size_t r = (size_t)blockIdx.x * slots + slot;
+    for (; r + 3 * stride < rows; r += 4 * stride) {   // four independent 16-byte loads in flight per thread
+      uint4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = __ldcs(reinterpret_cast<const uint4*>(x) + (r + j * stride) * cgs + cg);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        unpack8(v[j], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += f[k];
+      }
+    }
+    for (; r < rows; r += stride) {
       float f[8];
       unpack8(reinterpret_cast<const uint4*>(x)[r * cgs + cg], f);
 #pragma unroll
@@ -680,23 +710,30 @@ int cmu_bn_relu_bwd(const void* da, const void* dpool, const void* y, const floa
   // eval-mode BN is a fixed affine map: the batch-statistics terms of the backward vanish
   const float inv_count = training ? 1.f / ((float)n * h * w) : 0.f;
   const __nv_bfloat16 *pda = (const __nv_bfloat16*)da, *pdp = (const __nv_bfloat16*)dpool, *py = (const __nv_bfloat16*)y;
+  // One resident wave per launch: grid = SMs x blocks that fit per SM (a fixed 4 blocks/SM left the 80-register reduce
+  // kernel with a second wave at one-third occupancy: 3.8 TB/s instead of ~5.5).
+  const int sms = num_sms();
   if (dpool != nullptr) {
     CMU_REQUIRE(h % 2 == 0 && w % 2 == 0, "bn_relu_bwd: pooling needs even H, W");
-    bn_bwd_kernel<true, false><<<grid, 256, shmem, st>>>(pda, pdp, py, scale, shift, mean, rstd, nullptr, inv_count,
-                                                         partial, nullptr, n, h, w, c);
+    const int g = std::min(grid, sms * resident_blocks(bn_bwd_kernel<true, false>, 256, shmem));
+    bn_bwd_kernel<true, false><<<g, 256, shmem, st>>>(pda, pdp, py, scale, shift, mean, rstd, nullptr, inv_count,
+                                                      partial, nullptr, n, h, w, c);
+    CMU_LAUNCH_CHECK();
+    reduce_rows_kernel<<<ceil_div(2 * c, 32), 256, 0, st>>>(partial, sums, g, 2 * c, 0);
   } else {
-    bn_bwd_kernel<false, false><<<grid, 256, shmem, st>>>(pda, pdp, py, scale, shift, mean, rstd, nullptr, inv_count,
-                                                          partial, nullptr, n, h, w, c);
+    const int g = std::min(grid, sms * resident_blocks(bn_bwd_kernel<false, false>, 256, shmem));
+    bn_bwd_kernel<false, false><<<g, 256, shmem, st>>>(pda, pdp, py, scale, shift, mean, rstd, nullptr, inv_count,
+                                                       partial, nullptr, n, h, w, c);
+    CMU_LAUNCH_CHECK();
+    reduce_rows_kernel<<<ceil_div(2 * c, 32), 256, 0, st>>>(partial, sums, g, 2 * c, 0);
   }
   CMU_LAUNCH_CHECK();
-  reduce_rows_kernel<<<ceil_div(2 * c, 32), 256, 0, st>>>(partial, sums, grid, 2 * c, 0);
-  CMU_LAUNCH_CHECK();
   if (dpool != nullptr)
-    bn_bwd_kernel<true, true><<<grid * 4, 256, 0, st>>>(pda, pdp, py, scale, shift, mean, rstd, sums, inv_count, nullptr,
-                                                        (__nv_bfloat16*)dy, n, h, w, c);
+    bn_bwd_kernel<true, true><<<sms * resident_blocks(bn_bwd_kernel<true, true>, 256, 0), 256, 0, st>>>(
+        pda, pdp, py, scale, shift, mean, rstd, sums, inv_count, nullptr, (__nv_bfloat16*)dy, n, h, w, c);
   else
-    bn_bwd_kernel<false, true><<<grid * 4, 256, 0, st>>>(pda, pdp, py, scale, shift, mean, rstd, sums, inv_count,
-                                                         nullptr, (__nv_bfloat16*)dy, n, h, w, c);
+    bn_bwd_kernel<false, true><<<sms * resident_blocks(bn_bwd_kernel<false, true>, 256, 0), 256, 0, st>>>(
+        pda, pdp, py, scale, shift, mean, rstd, sums, inv_count, nullptr, (__nv_bfloat16*)dy, n, h, w, c);
   CMU_LAUNCH_CHECK();
   return 0;
 }

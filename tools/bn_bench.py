@@ -1,0 +1,49 @@
+"""Micro-benchmark of the HBM-bound BatchNorm backward / column-sum kernels at the benchmark shapes (CUDA events, L2 flushed).
+    python tools/bn_bench.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from contrastive_masked_unet_b200 import ops  # noqa: E402
+
+BF16 = torch.bfloat16
+
+
+def timeit(fn, flush, iters=7):
+    fn()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+def main():
+    dev = 'cuda'
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for B, S, C in ((64, 512, 64), (64, 256, 128), (64, 128, 256), (64, 64, 512)):
+        y = torch.randn(B, S, S, C, device=dev).to(BF16)
+        da = torch.randn(B, S, S, C, device=dev).to(BF16)
+        dp = torch.randn(B, S // 2, S // 2, C, device=dev).to(BF16)
+        scale, shift = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.1
+        mean, rstd = torch.randn(C, device=dev) * 0.1, torch.rand(C, device=dev) + 0.5
+        nbytes = y.numel() * 2
+        t1 = timeit(lambda: ops.bn_relu_bwd(da, None, y, scale, shift, mean, rstd), flush)
+        t2 = timeit(lambda: ops.bn_relu_bwd(da, dp, y, scale, shift, mean, rstd), flush)
+        t3 = timeit(lambda: ops.colsum_bf16(B * S * S, C, y), flush)
+        t4 = timeit(lambda: ops.bn_relu_apply(y, scale, shift, False), flush)
+        print(f'B{B} S{S} C{C}: bn_bwd {t1:.3f} ms ({5 * nbytes / t1 / 1e9:.2f} TB/s)  bn_bwd+pool {t2:.3f} ms '
+              f'({5.5 * nbytes / t2 / 1e9:.2f} TB/s)  colsum {t3:.3f} ms ({nbytes / t3 / 1e9:.2f} TB/s)  '
+              f'bn_relu {t4:.3f} ms ({2 * nbytes / t4 / 1e9:.2f} TB/s)', flush=True)
+
+
+if __name__ == '__main__':
+    main()
