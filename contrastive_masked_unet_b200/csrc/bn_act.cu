@@ -20,6 +20,10 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[2 * i + 1] = t.y;
   }
 }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 u;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
@@ -92,6 +96,48 @@ __global__ void __launch_bounds__(256) transpose_cast_kernel(const float* __rest
   for (int i = ty; i < 64; i += 4) {
     const long long c = c0 + i, r = r0 + tx;
     if (r < R && c < C) yt[c * R + r] = __float2bfloat16_rn(tile[tx][i]);
+  }
+}
+// same, 16-byte accesses on both sides (needs R % 8 == 0, C % 4 == 0 and 16-byte aligned pointers): float4 loads,
+// 8-byte stores of the plain copy, 16-byte (8 x bf16) stores of the transposed one
+__global__ void __launch_bounds__(256) transpose_cast_vec_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ yt,
+                                                                 __nv_bfloat16* __restrict__ y, long long R, long long C) {
+  __shared__ float tile[64][65];
+  const long long r0 = (long long)blockIdx.y * 64, c0 = (long long)blockIdx.x * 64;
+  const int q = threadIdx.x & 15, rr = threadIdx.x >> 4;   // 16 float4 per row, 16 rows per pass
+#pragma unroll
+  for (int pass = 0; pass < 4; ++pass) {
+    const int i = pass * 16 + rr;
+    const long long r = r0 + i, c = c0 + q * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < R && c < C) {
+      v = __ldcs(reinterpret_cast<const float4*>(x + r * C + c));
+      if (y != nullptr) {
+        uint2 pk;
+        pk.x = pack_bf16x2(v.x, v.y);
+        pk.y = pack_bf16x2(v.z, v.w);
+        *reinterpret_cast<uint2*>(y + r * C + c) = pk;
+      }
+    }
+    tile[i][q * 4 + 0] = v.x;
+    tile[i][q * 4 + 1] = v.y;
+    tile[i][q * 4 + 2] = v.z;
+    tile[i][q * 4 + 3] = v.w;
+  }
+  __syncthreads();
+  const int rb = threadIdx.x & 7, cc = threadIdx.x >> 3;   // 8 row blocks of 8, 32 columns per pass
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const int ci = pass * 32 + cc;
+    const long long c = c0 + ci, r = r0 + rb * 8;
+    if (c < C && r < R) {
+      uint4 pk;
+      pk.x = pack_bf16x2(tile[rb * 8 + 0][ci], tile[rb * 8 + 1][ci]);
+      pk.y = pack_bf16x2(tile[rb * 8 + 2][ci], tile[rb * 8 + 3][ci]);
+      pk.z = pack_bf16x2(tile[rb * 8 + 4][ci], tile[rb * 8 + 5][ci]);
+      pk.w = pack_bf16x2(tile[rb * 8 + 6][ci], tile[rb * 8 + 7][ci]);
+      *reinterpret_cast<uint4*>(yt + c * R + r) = pk;
+    }
   }
 }
 
@@ -624,7 +670,12 @@ int cmu_cast_f32_to_bf16(const float* x, void* y, long long n, void* stream) {
 int cmu_transpose_cast_bf16(const float* x, void* yt, void* y, long long rows, long long cols, void* stream) {
   dim3 grid((unsigned)((cols + 63) / 64), (unsigned)((rows + 63) / 64));
   CMU_REQUIRE(grid.y <= 65535, "transpose_cast: too many rows (%lld)", rows);
-  transpose_cast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)yt, (__nv_bfloat16*)y, rows, cols);
+  const bool vec = rows % 8 == 0 && cols % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)yt % 16 == 0) &&
+                   ((uintptr_t)y % 8 == 0);
+  if (vec)
+    transpose_cast_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)yt, (__nv_bfloat16*)y, rows, cols);
+  else
+    transpose_cast_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)yt, (__nv_bfloat16*)y, rows, cols);
   CMU_LAUNCH_CHECK();
   return 0;
 }

@@ -40,28 +40,44 @@ __global__ void __launch_bounds__(256) head1x1_fwd_kernel(const __nv_bfloat16* _
     w1[k] = w[64 + cg * 8 + k];
   }
   const float b0 = b[0], b1 = b[1];
-  const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 3;
-  const size_t npad = (npix + 3) & ~size_t(3);   // keep whole warps in the loop for the shuffles
-  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < npad; pix += stride) {
-    float f[8];
-    float d0 = 0.f, d1 = 0.f;
-    if (pix < npix) {
-      unpack8f(reinterpret_cast<const uint4*>(a)[pix * 8 + cg], f);
+  // a warp takes 32 consecutive pixels per iteration: 8 independent 16-byte loads per lane (4 pixels x 8 lanes each),
+  // 8-lane butterflies, then lane L collects pixel L so that both output planes get one coalesced 128-byte store
+  const uint32_t lane = threadIdx.x & 31;
+  const size_t warp_id = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t base = warp_id * 32; base < npix; base += n_warps * 32) {
+    uint4 raw[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const size_t pix = base + j * 4 + (lane >> 3);
+      raw[j] = (pix < npix) ? __ldcs(reinterpret_cast<const uint4*>(a) + pix * 8 + cg) : make_uint4(0, 0, 0, 0);
+    }
+    float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float f[8];
+      unpack8f(raw[j], f);
+      float d0 = 0.f, d1 = 0.f;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         d0 = fmaf(f[k], w0[k], d0);
         d1 = fmaf(f[k], w1[k], d1);
       }
-    }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-      d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+      for (int o = 4; o > 0; o >>= 1) {
+        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+      }
+      // pixel base + j*4 + q is complete in every lane of group q; lane L = j*4 + q fetches it
+      const float v0 = __shfl_sync(0xffffffffu, d0, (lane & 3) * 8);
+      const float v1 = __shfl_sync(0xffffffffu, d1, (lane & 3) * 8);
+      if ((int)(lane >> 2) == j) { m0 = v0; m1 = v1; }
     }
-    if (cg == 0 && pix < npix) {
+    const size_t pix = base + lane;
+    if (pix < npix) {
       const size_t n = pix / hw, p = pix % hw;
-      out[(n * 2 + 0) * hw + p] = d0 + b0;
-      out[(n * 2 + 1) * hw + p] = d1 + b1;
+      out[(n * 2 + 0) * hw + p] = m0 + b0;
+      out[(n * 2 + 1) * hw + p] = m1 + b1;
     }
   }
 }

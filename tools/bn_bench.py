@@ -45,5 +45,25 @@ def main():
               f'bn_relu {t4:.3f} ms ({2 * nbytes / t4 / 1e9:.2f} TB/s)', flush=True)
 
 
+def misc():
+    dev = 'cuda'
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    B, S = 64, 512
+    a = torch.randn(B, S, S, 64, device=dev).to(BF16)
+    w, b = torch.randn(2, 64, device=dev), torch.randn(2, device=dev)
+    dout = torch.randn(B, 2, S, S, device=dev)
+    nb = a.numel() * 2
+    t1 = timeit(lambda: ops.head1x1_fprop(a, w, b), flush)
+    t2 = timeit(lambda: ops.head1x1_bwd(a, w, dout), flush)
+    x = torch.randn(1536, S * S, device=dev)
+    t3 = timeit(lambda: ops.transpose_cast(x, False), flush)
+    t4 = timeit(lambda: ops.transpose_cast(x, True), flush)
+    xb = x.numel()
+    print(f'head1x1 fwd {t1:.3f} ms ({(nb + dout.numel() * 4) / t1 / 1e9:.2f} TB/s)  bwd {t2:.3f} ms '
+          f'({(2 * nb + dout.numel() * 4) / t2 / 1e9:.2f} TB/s)  transpose_cast {t3:.3f} ms ({6 * xb / t3 / 1e9:.2f} TB/s)  '
+          f'+plain {t4:.3f} ms ({8 * xb / t4 / 1e9:.2f} TB/s)', flush=True)
+
+
 if __name__ == '__main__':
+    misc()
     main()
