@@ -463,12 +463,25 @@ __global__ void __launch_bounds__(256, kPool ? 2 : 3) bn_bwd_kernel(const __nv_b
                                                      const float* __restrict__ rstd, const float* __restrict__ sums,
                                                      float inv_count, float* __restrict__ partial,
                                                      __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C) {
-  extern __shared__ float sacc[];  // [2][C] (reduce pass)
+  extern __shared__ float sacc[];  // [2][C] (reduce pass), then [6][C] per-channel constants (pooled variants)
   const int cgs = C >> 3;
+  // the pooled variants keep 4 pixels x 8 channels live per thread: their per-channel constants stay in shared memory
+  // (read as needed) instead of 48 registers, which otherwise spill under the 128-register cap of 2 blocks/SM
+  float* consts = sacc + (kApply ? 0 : 2 * C);
+  if (kPool) {
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+      consts[i] = scale[i];
+      consts[C + i] = shift[i];
+      consts[2 * C + i] = mean[i];
+      consts[3 * C + i] = rstd[i];
+      consts[4 * C + i] = kApply ? sums[i] * inv_count : 0.f;
+      consts[5 * C + i] = kApply ? sums[C + i] * inv_count : 0.f;
+    }
+  }
   if (!kApply) {
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sacc[i] = 0.f;
-    __syncthreads();
   }
+  if (kPool || !kApply) __syncthreads();
   // a block handles a fixed channel group per thread: threads are laid out [pixel-slot][cg] with cg fastest
   const int tpb = blockDim.x;
   const int slots = tpb / cgs > 0 ? tpb / cgs : 1;
@@ -476,7 +489,7 @@ __global__ void __launch_bounds__(256, kPool ? 2 : 3) bn_bwd_kernel(const __nv_b
   const int slot = threadIdx.x / cgs;
   const bool active = slot < slots && cgs <= tpb;
   float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8];
-  if (active) {
+  if (active && !kPool) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       sc[k] = scale[cg * 8 + k];
@@ -497,6 +510,7 @@ __global__ void __launch_bounds__(256, kPool ? 2 : 3) bn_bwd_kernel(const __nv_b
   if (active) {
     for (size_t u = (size_t)blockIdx.x * slots + slot; u < units; u += (size_t)gridDim.x * slots) {
       if (kPool) {
+        const float* cc = consts + cg * 8;
         const int wp = u % Wq;
         const int hp = (u / Wq) % Hq;
         const size_t nb = u / ((size_t)Wq * Hq);
@@ -520,7 +534,7 @@ __global__ void __launch_bounds__(256, kPool ? 2 : 3) bn_bwd_kernel(const __nv_b
           float zb[4];
 #pragma unroll
           for (int d = 0; d < 4; ++d)
-            zb[d] = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(yv[d][k], sc[k], sh[k]), 0.f)));
+            zb[d] = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(yv[d][k], cc[k], cc[C + k]), 0.f)));
           float m = zb[0];
           int w = 0;
 #pragma unroll
@@ -539,8 +553,8 @@ __global__ void __launch_bounds__(256, kPool ? 2 : 3) bn_bwd_kernel(const __nv_b
           for (int k = 0; k < 8; ++k) {
             const float gg = g[k] + (win[k] == d ? gp[k] : 0.f);
             const float dz = pos[d][k] ? gg : 0.f;
-            const float xh = (yv[d][k] - mu[k]) * rs[k];
-            if (kApply) o[k] = sc[k] * (dz - k1[k] - xh * k2[k]);
+            const float xh = (yv[d][k] - cc[2 * C + k]) * cc[3 * C + k];
+            if (kApply) o[k] = cc[k] * (dz - cc[4 * C + k] - xh * cc[5 * C + k]);
             else { a1[k] += dz; a2[k] += dz * xh; }
           }
           if (kApply) reinterpret_cast<uint4*>(dy)[pixs[d] * cgs + cg] = pack8(o);
@@ -766,8 +780,9 @@ int cmu_bn_relu_bwd(const void* da, const void* dpool, const void* y, const floa
   const int sms = num_sms();
   if (dpool != nullptr) {
     CMU_REQUIRE(h % 2 == 0 && w % 2 == 0, "bn_relu_bwd: pooling needs even H, W");
-    const int g = std::min(grid, sms * resident_blocks(bn_bwd_kernel<true, false>, 256, shmem));
-    bn_bwd_kernel<true, false><<<g, 256, shmem, st>>>(pda, pdp, py, scale, shift, mean, rstd, nullptr, inv_count,
+    const size_t shmem_p = 8 * (size_t)c * sizeof(float);
+    const int g = std::min(grid, sms * resident_blocks(bn_bwd_kernel<true, false>, 256, shmem_p));
+    bn_bwd_kernel<true, false><<<g, 256, shmem_p, st>>>(pda, pdp, py, scale, shift, mean, rstd, nullptr, inv_count,
                                                       partial, nullptr, n, h, w, c);
     CMU_LAUNCH_CHECK();
     reduce_rows_kernel<<<ceil_div(2 * c, 32), 256, 0, st>>>(partial, sums, g, 2 * c, 0);
@@ -780,7 +795,8 @@ int cmu_bn_relu_bwd(const void* da, const void* dpool, const void* y, const floa
   }
   CMU_LAUNCH_CHECK();
   if (dpool != nullptr)
-    bn_bwd_kernel<true, true><<<sms * resident_blocks(bn_bwd_kernel<true, true>, 256, 0), 256, 0, st>>>(
+    bn_bwd_kernel<true, true><<<sms * resident_blocks(bn_bwd_kernel<true, true>, 256, 6 * (size_t)c * sizeof(float)), 256,
+                                6 * (size_t)c * sizeof(float), st>>>(
         pda, pdp, py, scale, shift, mean, rstd, sums, inv_count, nullptr, (__nv_bfloat16*)dy, n, h, w, c);
   else
     bn_bwd_kernel<false, true><<<sms * resident_blocks(bn_bwd_kernel<false, true>, 256, 0), 256, 0, st>>>(
