@@ -106,13 +106,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
             if (leader) mbar_arrive_expect_tx(&full_bar[st], tx_pair);
             const uint32_t fb = mapa_u32(smem_u32(&full_bar[st]), 0);  // the leader's full barrier
             const int k0 = c << 6;
-            const bool second = k0 >= p.c0;
-            const CUtensorMap* src = second ? &p.tmA1 : &p.tmA0;
-            const int cc = second ? k0 - p.c0 : k0;
-            if (p.mode == MODE_CONV3)
-              tma_load_4d_pair(sA, src, fb, cc, w0 + s - 1, h0 - 1, img);
-            else
-              tma_load_4d_pair(sA, src, fb, cc, w0, h0, img);
+            if (p.mode == MODE_CONVT_DGRAD) {   // K = (r, s, co): gather dy at (2h + r, 2w + s) through the 5-D map
+              const int per = p.c0 >> 6;
+              const int rs = c / per;
+              const int cc = (c - rs * per) << 6;
+              tma_load_5d_pair(sA, &p.tmA0, fb, (rs & 1) * p.c0 + cc, w0, rs >> 1, h0, img);
+            } else {
+              const bool second = k0 >= p.c0;
+              const CUtensorMap* src = second ? &p.tmA1 : &p.tmA0;
+              const int cc = second ? k0 - p.c0 : k0;
+              if (p.mode == MODE_CONV3)
+                tma_load_4d_pair(sA, src, fb, cc, w0 + s - 1, h0 - 1, img);
+              else
+                tma_load_4d_pair(sA, src, fb, cc, w0, h0, img);
+            }
             tma_load_3d_pair(sB, &p.tmB, fb, k0, n0 + (int)rank * kHalfN, (p.mode == MODE_CONV3) ? 3 * s : 0);
           }
         }
@@ -235,8 +242,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
         __syncwarp();
         if (lane == 0) {
           const int nch = n0 + slab * 64;
-          if (nch < p.oc0) tma_store_4d(&p.tmO0, stg, nch, w0 + wtw0, h0 + wth0, img);
-          else tma_store_4d(&p.tmO1, stg, nch - p.oc0, w0 + wtw0, h0 + wth0, img);
+          if (p.mode == MODE_CONVT_FPROP) {   // N = (r, s, co): scatter to (2h + r, 2w + s)
+            const int rs = nch / p.oc0;
+            const int co = nch - rs * p.oc0;
+            tma_store_5d(&p.tmO0, stg, (rs & 1) * p.oc0 + co, w0 + wtw0, rs >> 1, h0 + wth0, img);
+          } else if (nch < p.oc0) {
+            tma_store_4d(&p.tmO0, stg, nch, w0 + wtw0, h0 + wth0, img);
+          } else {
+            tma_store_4d(&p.tmO1, stg, nch - p.oc0, w0 + wtw0, h0 + wth0, img);
+          }
           tma_store_commit();
         }
         if (p.stats != nullptr) slab_stats(stg, lane, valid_rows, &s_stats[slab * 64], &s_stats[BN + slab * 64]);
@@ -275,7 +289,8 @@ static int launch_pair(const K1Params& p, int grid, int smem_bytes, cudaStream_t
 int run_k1_pair(K1Params& p, const void* wpk, int ktot, cudaStream_t stream, int* used, int* used_bn) {
   *used = 0;
   if (debug_knob(5) == 1) return 0;
-  if (p.mode != MODE_CONV3 && p.mode != MODE_PLAIN) return 0;
+  const bool convT = (p.mode == MODE_CONVT_FPROP || p.mode == MODE_CONVT_DGRAD);
+  if (convT && debug_knob(11) == 1) return 0;                   // A/B: ConvTranspose on the 1-CTA kernel
   if (p.m_tiles < 2 * num_sms()) return 0;
   if (p.n_total % 128 != 0 && debug_knob(7) == 1) return 0;   // A/B: 64-wide layers on the 1-CTA kernel
   const int BN = (p.n_total % 256 == 0 && debug_knob(6) != 1) ? 256 : (p.n_total % 128 == 0 ? 128 : 64);

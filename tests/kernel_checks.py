@@ -605,6 +605,8 @@ CHECKS = {
     'conv3x3_wgrad_only_128_128': lambda: check_conv3x3_wgrad_only(2, 16, 16, 128, 0, 128, seed=1),
     'conv3x3_c1': check_conv3x3_c1,
     'convT_128_64': lambda: check_convT(2, 12, 20, 128, 64),
+    'convT_256_128_pair_ragged': lambda: check_convT(3, 120, 136, 256, 128, seed=15),
+    'convT_512_256_pair': lambda: check_convT(17, 32, 32, 512, 256, seed=16),
     'convT_1024_512': lambda: check_convT(2, 4, 4, 1024, 512, seed=12),
     'convT_256_128_ragged': lambda: check_convT(2, 14, 14, 256, 128, seed=13),
     'conv1x1_1024_256': check_conv1x1,
