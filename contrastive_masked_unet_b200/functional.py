@@ -183,7 +183,12 @@ class LinearFn(torch.autograd.Function):
     matrix rows" GEMMs once the small operand is transposed; small layers use the fp32 SIMT SGEMM."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, exchange=False):
+        """exchange=True (data parallel, weight excluded from DDP's all-reduce): the weight gradient of a linear layer is
+        the rank-(global batch) product dy^T x, so the ranks all-gather the two thin factors (M x N and M x K) and each
+        computes the already-averaged dW locally -- for projector.fc0 (1536 x S^2 = 1.6 GB of fp32 gradient at S = 512)
+        that replaces a 1.6 GB all-reduce by a 34 MB/rank all-gather; the result is identical on every rank."""
+        ctx.exchange = bool(exchange) and _world() > 1
         x = x.contiguous().float()
         w = weight.detach().contiguous().float()
         m, k = x.shape
@@ -212,12 +217,25 @@ class LinearFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = ops.gemm_tn(dyt16, w)                                 # (M,K) = dy W
             if ctx.needs_input_grad[1]:
+                if ctx.exchange:
+                    dy16, x = _gather_rows(dy16), _gather_rows(x)
                 dw = ops.gemm_tn(dy16, x)                                  # (N,K) = dy^T x
         else:
             dx = ops.linear_dgrad(dy, w) if ctx.needs_input_grad[0] else None
-            dw = ops.linear_wgrad(dy, x) if ctx.needs_input_grad[1] else None
+            if ctx.needs_input_grad[1]:
+                dw = ops.linear_wgrad(_gather_rows(dy), _gather_rows(x)) if ctx.exchange else ops.linear_wgrad(dy, x)
+        if dw is not None and ctx.exchange:
+            dw = dw / _world()                                             # DDP averages gradients over the ranks
         db = ops.colsum(dy) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
-        return dx, dw, db
+        return dx, dw, db, None
+
+
+def _gather_rows(t):
+    """(M, C) on every rank -> (world*M, C), rank-major (no gradient)."""
+    t = t.contiguous()
+    out = torch.empty(_world() * t.shape[0], t.shape[1], dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t)
+    return out
 
 
 def _world(group=None):
