@@ -600,6 +600,10 @@ CHECKS = {
     'conv3x3_pair_64_128': lambda: check_conv3x3(6, 128, 128, 64, 0, 128, seed=33),
     'conv3x3_pair_64_64': lambda: check_conv3x3(6, 128, 128, 64, 0, 64, seed=34),
     'conv3x3_pair_cat_64+64_64': lambda: check_conv3x3(5, 136, 120, 64, 64, 64, seed=35),
+    # BASELINE.json configs[1] full sizes (per-GPU batch 64 @512^2): first-level and bottleneck-level layers
+    'conv3x3_full_size_enc1_conv2': lambda: check_conv3x3(64, 512, 512, 64, 0, 64, seed=50),
+    'conv3x3_full_size_up4_conv1': lambda: check_conv3x3(64, 64, 64, 512, 512, 512, seed=51),
+    'convT_full_size_up1': lambda: check_convT(64, 256, 256, 128, 64, seed=52),
     'conv3x3_fprop_only_64_64': lambda: check_conv3x3_fprop_only(2, 24, 40, 64, 0, 64),
     'conv3x3_wgrad_only_64_64': lambda: check_conv3x3_wgrad_only(2, 24, 40, 64, 0, 64),
     'conv3x3_wgrad_only_128_128': lambda: check_conv3x3_wgrad_only(2, 16, 16, 128, 0, 128, seed=1),
