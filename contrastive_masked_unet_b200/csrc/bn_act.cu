@@ -150,17 +150,18 @@ __global__ void __launch_bounds__(256) transpose_cast_vec_kernel(const float* __
 constexpr int kC1Cout = 64;
 constexpr int kC1MaxW = 2048;
 
-__device__ __forceinline__ void c1_stage_rows(float (*srow)[kC1MaxW + 2], const float* __restrict__ x,
+constexpr int kC1Rows = 4;   // output rows per staging round: kC1Rows + 2 masked input rows are staged once
+__device__ __forceinline__ void c1_stage_rows(float* srow, int pitch, const float* __restrict__ x,
                                               const uint8_t* __restrict__ mask0, int nb, int h, int H, int W) {
-  for (int i = threadIdx.x; i < 3 * (W + 2); i += blockDim.x) {
-    const int r = i / (W + 2), c = i - r * (W + 2);
+  for (int i = threadIdx.x; i < (kC1Rows + 2) * pitch; i += blockDim.x) {
+    const int r = i / pitch, c = i - r * pitch;
     const int hh = h + r - 1, ww = c - 1;
     float v = 0.f;
     if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
       v = __ldg(x + ((size_t)nb * H + hh) * W + ww);
       if (mask0 != nullptr && mask0[hh * W + ww]) v = 0.f;
     }
-    srow[r][c] = v;
+    srow[i] = v;
   }
 }
 
@@ -168,7 +169,8 @@ __global__ void __launch_bounds__(256) conv_c1_fprop_kernel(const float* __restr
                                                             const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
                                                             float* __restrict__ stats_partial, int N, int H, int W) {
   extern __shared__ float c1_smem[];
-  float (*srow)[kC1MaxW + 2] = reinterpret_cast<float (*)[kC1MaxW + 2]>(c1_smem);
+  float* srow = c1_smem;
+  const int pitch = W + 2;
   __shared__ float sw[kC1Cout * 9];
   __shared__ float sred[2][kC1Cout];
   for (int i = threadIdx.x; i < kC1Cout * 9; i += blockDim.x) sw[i] = w[i];
@@ -176,42 +178,60 @@ __global__ void __launch_bounds__(256) conv_c1_fprop_kernel(const float* __restr
   __syncthreads();
   const int cg = threadIdx.x & 7;   // channel group: channels cg*8 .. cg*8+7
   const int px = threadIdx.x >> 3;  // 32 pixels per pass
-  float wr[8][9];
+  // packed fp32 math (sm_100 FFMA2): one instruction per channel PAIR; each lane is an ordinary IEEE fma, so the
+  // results are bit-identical to the scalar loop
+  float2 wr[4][9];
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
-    for (int t = 0; t < 9; ++t) wr[c][t] = sw[(cg * 8 + c) * 9 + t];
-  float s1[8], s2[8];
+    for (int t = 0; t < 9; ++t) wr[c][t] = make_float2(sw[(cg * 8 + 2 * c) * 9 + t], sw[(cg * 8 + 2 * c + 1) * 9 + t]);
+  float2 s1p[4], s2p[4];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) s1[c] = s2[c] = 0.f;
-  const int rows = N * H;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int nb = row / H, h = row - nb * H;
+  for (int c = 0; c < 4; ++c) s1p[c] = s2p[c] = make_float2(0.f, 0.f);
+  const int hgroups = (H + kC1Rows - 1) / kC1Rows;
+  const int groups = N * hgroups;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int nb = grp / hgroups, h0 = (grp - nb * hgroups) * kC1Rows;
     __syncthreads();
-    c1_stage_rows(srow, x, mask0, nb, h, H, W);
+    c1_stage_rows(srow, pitch, x, mask0, nb, h0, H, W);
     __syncthreads();
-    uint4* yrow = reinterpret_cast<uint4*>(y) + (size_t)row * W * 8;
-    for (int w0 = 0; w0 < W; w0 += 32) {
-      const int wq = w0 + px;
-      if (wq < W) {
-        float xin[9];
+    for (int rr = 0; rr < kC1Rows && h0 + rr < H; ++rr) {
+      uint4* yrow = reinterpret_cast<uint4*>(y) + ((size_t)nb * H + h0 + rr) * W * 8;
+      const float* sr = srow + rr * pitch;
+      for (int w0 = 0; w0 < W; w0 += 32) {
+        const int wq = w0 + px;
+        if (wq < W) {
+          float2 xin[9];
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+          for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int s = 0; s < 3; ++s) xin[r * 3 + s] = srow[r][wq + s];
-        float o[8];
+            for (int s = 0; s < 3; ++s) {
+              const float v = sr[r * pitch + wq + s];
+              xin[r * 3 + s] = make_float2(v, v);
+            }
+          float o[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float a = 0.f;
+          for (int c = 0; c < 4; ++c) {
+            float2 a = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int t = 0; t < 9; ++t) a = fmaf(wr[c][t], xin[t], a);
-          o[c] = a;
-          s1[c] += a;
-          s2[c] += a * a;
+            for (int t = 0; t < 9; ++t) a = __ffma2_rn(wr[c][t], xin[t], a);
+            o[2 * c] = a.x;
+            o[2 * c + 1] = a.y;
+            s1p[c] = __fadd2_rn(s1p[c], a);
+            s2p[c] = __ffma2_rn(a, a, s2p[c]);
+          }
+          yrow[wq * 8 + cg] = pack8(o);
         }
-        yrow[wq * 8 + cg] = pack8(o);
       }
     }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    s1[2 * c] = s1p[c].x;
+    s1[2 * c + 1] = s1p[c].y;
+    s2[2 * c] = s2p[c].x;
+    s2[2 * c + 1] = s2p[c].y;
   }
   if (stats_partial != nullptr) {
 #pragma unroll
@@ -237,40 +257,58 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restr
                                                             const __nv_bfloat16* __restrict__ dy, float* __restrict__ partial,
                                                             int N, int H, int W) {
   extern __shared__ float c1_smem[];
-  float (*srow)[kC1MaxW + 2] = reinterpret_cast<float (*)[kC1MaxW + 2]>(c1_smem);
+  float* srow = c1_smem;
+  const int pitch = W + 2;
   __shared__ float sred[kC1Cout * 9];
   for (int i = threadIdx.x; i < kC1Cout * 9; i += blockDim.x) sred[i] = 0.f;
   const int cg = threadIdx.x & 7;
   const int px = threadIdx.x >> 3;
-  float acc[8][9];
+  float2 acc2[4][9];   // channel pairs: packed fp32 FMA (FFMA2), bit-identical to the scalar accumulation
 #pragma unroll
-  for (int c = 0; c < 8; ++c)
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
-    for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
-  const int rows = N * H;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int nb = row / H, h = row - nb * H;
+    for (int t = 0; t < 9; ++t) acc2[c][t] = make_float2(0.f, 0.f);
+  const int hgroups = (H + kC1Rows - 1) / kC1Rows;
+  const int groups = N * hgroups;
+  for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const int nb = grp / hgroups, h0 = (grp - nb * hgroups) * kC1Rows;
     __syncthreads();
-    c1_stage_rows(srow, x, mask0, nb, h, H, W);
+    c1_stage_rows(srow, pitch, x, mask0, nb, h0, H, W);
     __syncthreads();
-    const uint4* grow = reinterpret_cast<const uint4*>(dy) + (size_t)row * W * 8;
-    for (int w0 = 0; w0 < W; w0 += 32) {
-      const int wq = w0 + px;
-      if (wq < W) {
-        float xin[9];
+    for (int rr = 0; rr < kC1Rows && h0 + rr < H; ++rr) {
+      const uint4* grow = reinterpret_cast<const uint4*>(dy) + ((size_t)nb * H + h0 + rr) * W * 8;
+      const float* sr = srow + rr * pitch;
+      for (int w0 = 0; w0 < W; w0 += 32) {
+        const int wq = w0 + px;
+        if (wq < W) {
+          float2 xin[9];
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+          for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int s = 0; s < 3; ++s) xin[r * 3 + s] = srow[r][wq + s];
-        float g[8];
-        unpack8(grow[wq * 8 + cg], g);
+            for (int s = 0; s < 3; ++s) {
+              const float v = sr[r * pitch + wq + s];
+              xin[r * 3 + s] = make_float2(v, v);
+            }
+          float g[8];
+          unpack8(__ldcs(grow + wq * 8 + cg), g);
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+          for (int c = 0; c < 4; ++c) {
+            const float2 gp = make_float2(g[2 * c], g[2 * c + 1]);
 #pragma unroll
-          for (int t = 0; t < 9; ++t) acc[c][t] = fmaf(g[c], xin[t], acc[c][t]);
+            for (int t = 0; t < 9; ++t) acc2[c][t] = __ffma2_rn(gp, xin[t], acc2[c][t]);
+          }
+        }
       }
     }
   }
+  float acc[8][9];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      acc[2 * c][t] = acc2[c][t].x;
+      acc[2 * c + 1][t] = acc2[c][t].y;
+    }
   __syncthreads();
 #pragma unroll
   for (int c = 0; c < 8; ++c)
@@ -700,7 +738,13 @@ int cmu_conv3x3_c1_fprop(const float* x, const unsigned char* mask0, const float
                          float* stats_partial, int n, int h, int wd, void* stream) {
   CMU_REQUIRE(cout == kC1Cout, "conv3x3_c1: Cout must be 64 (got %d)", cout);
   CMU_REQUIRE(wd <= kC1MaxW, "conv3x3_c1: image width %d exceeds %d", wd, kC1MaxW);
-  const int c1_shmem = 3 * (kC1MaxW + 2) * (int)sizeof(float);
+  const int c1_shmem = (kC1Rows + 2) * (wd + 2) * (int)sizeof(float);
+  static bool attr_f = false;
+  if (!attr_f) {
+    CMU_CHECK_CUDA(cudaFuncSetAttribute(conv_c1_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (kC1Rows + 2) * (kC1MaxW + 2) * (int)sizeof(float)));
+    attr_f = true;
+  }
   conv_c1_fprop_kernel<<<cmu_conv3x3_c1_grid(), 256, c1_shmem, (cudaStream_t)stream>>>(x, mask0, w, (__nv_bfloat16*)y,
                                                                                       stats_partial, n, h, wd);
   CMU_LAUNCH_CHECK();
@@ -712,7 +756,13 @@ int cmu_conv3x3_c1_wgrad(const float* x, const unsigned char* mask0, const void*
   CMU_REQUIRE(cout == kC1Cout, "conv3x3_c1: Cout must be 64 (got %d)", cout);
   const int grid = cmu_conv3x3_c1_grid();
   CMU_REQUIRE(wd <= kC1MaxW, "conv3x3_c1: image width %d exceeds %d", wd, kC1MaxW);
-  const int c1_shmem = 3 * (kC1MaxW + 2) * (int)sizeof(float);
+  const int c1_shmem = (kC1Rows + 2) * (wd + 2) * (int)sizeof(float);
+  static bool attr_w = false;
+  if (!attr_w) {
+    CMU_CHECK_CUDA(cudaFuncSetAttribute(conv_c1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (kC1Rows + 2) * (kC1MaxW + 2) * (int)sizeof(float)));
+    attr_w = true;
+  }
   conv_c1_wgrad_kernel<<<grid, 256, c1_shmem, (cudaStream_t)stream>>>(x, mask0, (const __nv_bfloat16*)dy, partial, n, h, wd);
   CMU_LAUNCH_CHECK();
   reduce_rows_kernel<<<ceil_div(kC1Cout * 9, 32), 256, 0, (cudaStream_t)stream>>>(partial, dw, grid, kC1Cout * 9,

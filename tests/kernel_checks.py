@@ -608,6 +608,8 @@ CHECKS = {
     'conv3x3_wgrad_only_64_64': lambda: check_conv3x3_wgrad_only(2, 24, 40, 64, 0, 64),
     'conv3x3_wgrad_only_128_128': lambda: check_conv3x3_wgrad_only(2, 16, 16, 128, 0, 128, seed=1),
     'conv3x3_c1': check_conv3x3_c1,
+    'conv3x3_c1_ragged_rows': lambda: check_conv3x3_c1(2, 30, 52, seed=2),   # H % 4 != 0, W % 32 != 0
+    'conv3x3_c1_224': lambda: check_conv3x3_c1(2, 224, 224, seed=3),
     'convT_128_64': lambda: check_convT(2, 12, 20, 128, 64),
     'convT_256_128_pair_ragged': lambda: check_convT(3, 120, 136, 256, 128, seed=15),
     'convT_512_256_pair': lambda: check_convT(17, 32, 32, 512, 256, seed=16),

@@ -59,6 +59,12 @@ def misc():
     t3 = timeit(lambda: ops.transpose_cast(x, False), flush)
     t4 = timeit(lambda: ops.transpose_cast(x, True), flush)
     xb = x.numel()
+    img = torch.randn(B, S, S, device=dev)
+    mask0 = (torch.rand(S, S, device=dev) > 0.35).to(torch.uint8)
+    w1 = torch.randn(64, 1, 3, 3, device=dev) * 0.3
+    t5 = timeit(lambda: ops.conv3x3_c1_fprop(img, mask0, w1), flush)
+    t6 = timeit(lambda: ops.conv3x3_c1_wgrad(img, mask0, a), flush)
+    print(f'conv_c1 fprop {t5:.3f} ms ({nb / t5 / 1e9:.2f} TB/s)  wgrad {t6:.3f} ms ({nb / t6 / 1e9:.2f} TB/s)', flush=True)
     print(f'head1x1 fwd {t1:.3f} ms ({(nb + dout.numel() * 4) / t1 / 1e9:.2f} TB/s)  bwd {t2:.3f} ms '
           f'({(2 * nb + dout.numel() * 4) / t2 / 1e9:.2f} TB/s)  transpose_cast {t3:.3f} ms ({6 * xb / t3 / 1e9:.2f} TB/s)  '
           f'+plain {t4:.3f} ms ({8 * xb / t4 / 1e9:.2f} TB/s)', flush=True)
