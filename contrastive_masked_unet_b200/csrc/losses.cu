@@ -98,28 +98,50 @@ __global__ void __launch_bounds__(256) head1x1_bwd_kernel(const __nv_bfloat16* _
     g0[k] = g1[k] = 0.f;
   }
   float s0 = 0.f, s1 = 0.f;
-  const size_t stride = ((size_t)gridDim.x * blockDim.x) >> 3;
-  for (size_t pix = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3; pix < npix; pix += stride) {
-    const size_t n = pix / hw, p = pix % hw;
-    const float d0 = __ldg(dout + (n * 2 + 0) * hw + p);
-    const float d1 = __ldg(dout + (n * 2 + 1) * hw + p);
-    float f[8], o[8];
-    unpack8f(reinterpret_cast<const uint4*>(a)[pix * 8 + cg], f);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      o[k] = d0 * w0[k] + d1 * w1[k];
-      g0[k] = fmaf(d0, f[k], g0[k]);
-      g1[k] = fmaf(d1, f[k], g1[k]);
+  // a warp takes 32 consecutive pixels per iteration: lane L fetches dout of pixel L (two coalesced 128-byte loads),
+  // every lane issues its 8 independent 16-byte loads of `a` (4 pixels x 8 lanes per step), dout is handed round by shuffle
+  const uint32_t lane = threadIdx.x & 31;
+  const size_t warp_id = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t base = warp_id * 32; base < npix; base += n_warps * 32) {
+    float dl0 = 0.f, dl1 = 0.f;
+    {
+      const size_t pix = base + lane;
+      if (pix < npix) {
+        const size_t n = pix / hw, p = pix % hw;
+        dl0 = __ldg(dout + (n * 2 + 0) * hw + p);
+        dl1 = __ldg(dout + (n * 2 + 1) * hw + p);
+      }
     }
-    uint4 pk;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+    uint4 raw[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
-    reinterpret_cast<uint4*>(da)[pix * 8 + cg] = pk;
-    if (cg == 0) {
-      s0 += d0;
-      s1 += d1;
+    for (int j = 0; j < 8; ++j) {
+      const size_t pix = base + j * 4 + (lane >> 3);
+      raw[j] = (pix < npix) ? __ldcs(reinterpret_cast<const uint4*>(a) + pix * 8 + cg) : make_uint4(0, 0, 0, 0);
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const size_t pix = base + j * 4 + (lane >> 3);
+      const float d0 = __shfl_sync(0xffffffffu, dl0, j * 4 + (lane >> 3));
+      const float d1 = __shfl_sync(0xffffffffu, dl1, j * 4 + (lane >> 3));
+      float f[8], o[8];
+      unpack8f(raw[j], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        o[k] = d0 * w0[k] + d1 * w1[k];
+        g0[k] = fmaf(d0, f[k], g0[k]);     // out-of-range pixels carry d = 0 and f = 0
+        g1[k] = fmaf(d1, f[k], g1[k]);
+      }
+      if (pix < npix) {
+        uint4 pk;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
+        reinterpret_cast<uint4*>(da)[pix * 8 + cg] = pk;
+      }
+    }
+    s0 += dl0;    // every pixel's dout is held by exactly one lane
+    s1 += dl1;
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
