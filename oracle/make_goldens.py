@@ -163,6 +163,33 @@ def gold_finetune(seed=0):
     return rec
 
 
+def gold_moco(seed=7, N=64, S=32, K=1024, steps=2):
+    """BASELINE.json configs[3] scaled down: the reference Moco_v2 (moco2_module.py) for two training steps on CPU, with a
+    plain SGD step on encoder_q in between so that the momentum update of the second step is non-trivial."""
+    from oracle.moco_oracle import moco_inputs
+    mm = ref_loader.import_moco()
+    torch.manual_seed(seed)
+    mod = mm.Moco_v2(emb_dim=1024, num_negatives=K, batch_size=N).train()
+    rec = {'seed': seed, 'N': N, 'S': S, 'K': K, 'init_q': _fp_named(mod.encoder_q.named_parameters()),
+           'init_queue': fingerprint(mod.queue), 'steps': []}
+    for step in range(steps):
+        img_q, img_k = moco_inputs(N, S, step)
+        mod.zero_grad()
+        mod._momentum_update_key_encoder()                                  # training_step, moco2_module.py:297
+        logits, labels, keys, _ = mod(img_q=img_q, img_k=img_k, queue=mod.queue)
+        loss = mod._compute_l_s(logits, labels, keys, queue=mod.queue)        # enqueue + cross-entropy
+        loss.backward()
+        rec['steps'].append({'loss': float(loss), 'logits': fingerprint(logits), 'keys': fingerprint(keys),
+                             'labels_dtype': str(labels.dtype), 'queue_ptr': int(mod.queue_ptr),
+                             'queue': fingerprint(mod.queue),
+                             'grad_q': _fp_named((k, p.grad) for k, p in mod.encoder_q.named_parameters()),
+                             'enc_k': _fp_named(mod.encoder_k.named_parameters())})
+        with torch.no_grad():
+            for p in mod.encoder_q.parameters():
+                p -= 0.05 * p.grad
+    return rec
+
+
 def gold_cldice():
     """FT/metrics.py:401-430 soft_cldice (the eval metric of FT/train.py:464) on deterministic synthetic inputs."""
     from oracle.cmunet_oracle import cldice_inputs
@@ -193,6 +220,9 @@ def main():
     if 'modules' in which:
         json.dump({'meta': meta, 'cases': gold_modules()}, open(os.path.join(GOLD, 'modules.json'), 'w'), indent=1)
         print('modules done')
+    if 'moco' in which:
+        json.dump({'meta': meta, 'case': gold_moco()}, open(os.path.join(GOLD, 'moco.json'), 'w'), indent=1)
+        print('moco done')
     if 'cldice' in which:
         json.dump({'meta': meta, 'cases': gold_cldice()}, open(os.path.join(GOLD, 'cldice.json'), 'w'), indent=1)
         print('cldice done')

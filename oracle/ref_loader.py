@@ -119,6 +119,34 @@ def import_finetune():
     return model, metrics
 
 
+def import_moco():
+    """Reference Pretraining/MoCo/pl_bolts/models/self_supervised/moco/moco2_module.py, unmodified, loaded by path with
+    stand-ins for what this container lacks: pytorch_lightning (oracle/ref_shim/pytorch_lightning), wandb, and the parts
+    of the vendored pl_bolts tree the module imports but that are absent or unimportable."""
+    _ensure_paths()
+    moco_dir = os.path.join(REF_ROOT, 'Pretraining', 'MoCo', 'pl_bolts', 'models', 'self_supervised', 'moco')
+
+    def stub(name, **attrs):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            sys.modules[name] = m
+        for k, v in attrs.items():
+            setattr(sys.modules[name], k, v)
+        return sys.modules[name]
+
+    stub('wandb')
+    stub('pl_bolts')
+    stub('pl_bolts.metrics', mean=lambda *a, **k: None, precision_at_k=lambda *a, **k: None)
+    stub('pl_bolts.utils', _TORCHVISION_AVAILABLE=True, _PIL_AVAILABLE=True)
+    stub('pl_bolts.utils.warnings', warn_missing_pkg=lambda *a, **k: None)
+    stub('transforms', Moco2EvalImagenetTransforms=object, Moco2TrainImagenetTransforms=object)   # data transforms: unused
+    if moco_dir not in sys.path:
+        sys.path.insert(0, moco_dir)
+    import importlib
+    return importlib.import_module('moco2_module')
+
+
 @contextlib.contextmanager
 def seeded(seed):
     import numpy as np

@@ -312,6 +312,46 @@ def moco_parity(N=64, S=64, K=4096, seed=7, steps=2):
     return rep
 
 
+def moco_vs_golden():
+    """The drop-in Moco_v2 on the GPU against tests/golden/moco.json (minted from the unmodified reference): same seed ->
+    same default-init weights and queue; two training steps with the same SGD update in between."""
+    from oracle import moco_oracle as MO
+    c = json.load(open(os.path.join(GOLD, 'moco.json')))['case']
+    torch.manual_seed(c['seed'])
+    m = C.Moco_v2(emb_dim=1024, num_negatives=c['K']).train()      # built on the CPU: RNG order of the reference constructor
+    rep = {'init_queue_sum': (float(m.queue.double().sum()), c['init_queue']['sum']), 'steps': [], 'fails': []}
+    if abs(rep['init_queue_sum'][0] - rep['init_queue_sum'][1]) > 1e-6 * max(1.0, abs(rep['init_queue_sum'][1])):
+        rep['fails'].append(f'queue init differs: {rep["init_queue_sum"]}')
+    k0 = 'down_conv1.double_conv.double_conv.0.weight'
+    w0 = dict(m.encoder_q.named_parameters())[k0]
+    if abs(float(w0.double().norm()) - c['init_q'][k0]['norm']) > 1e-6 * c['init_q'][k0]['norm']:
+        rep['fails'].append('encoder init differs from the reference constructor')
+    m = m.to(DEV)
+    for step, gs in enumerate(c['steps']):
+        img_q, img_k = MO.moco_inputs(c['N'], c['S'], step)
+        for p in m.encoder_q.parameters():
+            p.grad = None
+        loss = m.training_step(img_q.to(DEV), img_k.to(DEV))
+        loss.backward()
+        torch.cuda.synchronize()
+        rec = {'loss': (float(loss), gs['loss']), 'ptr': (int(m.queue_ptr), gs['queue_ptr']),
+               'queue_norm': (float(m.queue.double().norm()), gs['queue']['norm'])}
+        # loss: the first step starts from q == k (identical encoders), loss ~ 0.02 is dominated by bf16 rounding of the
+        # positive logit / T; compare absolutely there and relatively afterwards
+        tol = max(1e-2 * abs(gs['loss']), 2e-2)
+        if abs(rec['loss'][0] - rec['loss'][1]) > tol:
+            rep['fails'].append(f'step {step}: loss {rec["loss"]}')
+        if rec['ptr'][0] != rec['ptr'][1]:
+            rep['fails'].append(f'step {step}: queue_ptr {rec["ptr"]}')
+        if abs(rec['queue_norm'][0] - rec['queue_norm'][1]) > 1e-3 * rec['queue_norm'][1]:
+            rep['fails'].append(f'step {step}: queue norm {rec["queue_norm"]}')
+        rep['steps'].append(rec)
+        with torch.no_grad():
+            for p in m.encoder_q.parameters():
+                p -= 0.05 * p.grad
+    return rep
+
+
 def golden_pretrain(S, B):
     for c in json.load(open(os.path.join(GOLD, 'pretrain.json')))['cases']:
         if c['S'] == S and c['B'] == B:

@@ -107,3 +107,11 @@ def test_moco_queue_head_two_steps_vs_oracle():
     from tests import model_checks as M
     rep = M.moco_parity(64, 64, 4096)
     assert not rep['fails'], rep
+
+
+def test_moco_two_steps_vs_reference_golden():
+    """configs[3] scaled down, against values minted from the unmodified reference Moco_v2 (tests/golden/moco.json)."""
+    _gpu()
+    from tests import model_checks as M
+    rep = M.moco_vs_golden()
+    assert not rep['fails'], rep

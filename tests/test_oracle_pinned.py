@@ -128,9 +128,38 @@ def test_module_head():
     check_fp(ps.grad, c['d_proj_s'], rtol=1e-3)
 
 
+def test_moco_oracle_matches_reference_golden():
+    """OracleMoco (moco2_module.py restated) against tests/golden/moco.json, minted by running the unmodified reference
+    Moco_v2 for two training steps (oracle/make_goldens.py gold_moco)."""
+    from oracle import moco_oracle as MO
+    c = json.load(open(os.path.join(G, 'moco.json')))['case']
+    torch.manual_seed(c['seed'])
+    m = MO.OracleMoco(emb_dim=1024, num_negatives=c['K']).train()
+    for k, p in m.encoder_q.named_parameters():
+        check_fp(p, c['init_q'][k], rtol=1e-6)
+    check_fp(m.queue, c['init_queue'], rtol=1e-6)
+    for step, gs in enumerate(c['steps']):
+        img_q, img_k = MO.moco_inputs(c['N'], c['S'], step)
+        m.zero_grad()
+        loss, logits, keys = m.training_step(img_q, img_k)
+        loss.backward()
+        assert float(loss) == pytest.approx(gs['loss'], rel=1e-4)
+        check_fp(logits, gs['logits'])
+        check_fp(keys, gs['keys'])
+        assert int(m.queue_ptr) == gs['queue_ptr']
+        check_fp(m.queue, gs['queue'])
+        for k, p in m.encoder_q.named_parameters():
+            if not (k.endswith('double_conv.0.bias') or k.endswith('double_conv.3.bias')):   # analytically zero grads
+                check_fp(p.grad, gs['grad_q'][k], rtol=2e-3)
+        for k, p in m.encoder_k.named_parameters():
+            check_fp(p, gs['enc_k'][k], rtol=1e-5)
+        with torch.no_grad():
+            for p in m.encoder_q.parameters():
+                p -= 0.05 * p.grad
+
+
 def test_moco_oracle_self_consistency():
-    """oracle/moco_oracle.py is UNPINNED (reference MoCo needs pytorch-lightning); check its algebra against a manual
-    log-sum-exp and the enqueue pointer arithmetic of moco2_module.py:160-175."""
+    """moco_loss algebra against a manual log-sum-exp and the enqueue pointer arithmetic of moco2_module.py:160-175."""
     from oracle import moco_oracle as MO
     g = torch.Generator().manual_seed(3)
     q = torch.randn(8, 32, generator=g)
