@@ -239,8 +239,8 @@ def finetune_parity(B=4, S=256, seed=0, golden=None, grad_cos=0.999):
 
 
 def moco_parity(N=64, S=64, K=4096, seed=7, steps=2):
-    """configs[3] (MoCo-v2 queue head): K2 training steps of the drop-in against oracle/moco_oracle.py (parity unpinned:
-    the reference module needs pytorch-lightning, see the oracle header)."""
+    """configs[3] (MoCo-v2 queue head): two training steps of the drop-in against oracle/moco_oracle.py (pinned to the
+    reference by tests/golden/moco.json): loss, encoder_q gradients, EMA of encoder_k, queue contents."""
     from oracle import moco_oracle as MO
     torch.manual_seed(seed)
     m = C.Moco_v2(emb_dim=1024, num_negatives=K).to(DEV).train()
