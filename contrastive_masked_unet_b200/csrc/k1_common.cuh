@@ -35,33 +35,14 @@ struct K1Params {
   float* stats;     // [gridDim.x][2][BN] partial (sum, sum of squares) or nullptr
 };
 
-template <int OFF>
-__device__ __forceinline__ void bfly(float (&v)[32], uint32_t lane) {
-  const bool up = (lane & OFF) != 0;
-#pragma unroll
-  for (int i = 0; i < OFF; ++i) {
-    const float send = up ? v[i] : v[i + OFF];
-    const float keep = up ? v[i + OFF] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
-  }
-}
-// After the call, lane L holds in v[0] the sum over the 32 lanes of their v[L].
 // staging / epilogue-group plan: two groups with two 16 KB buffers each when the pipeline keeps >= 4 stages, then two
-// groups with one buffer, else the single-group plans.  (Short-K layers -- 64 channels, ConvTranspose, 1x1 -- are
-// bound by the epilogue's dependent-issue latency with one warp per scheduler; they have the shared memory to spare.)
+// groups with one buffer, else the single-group plans.  (Measured: the second group only helps ConvTranspose fprop,
+// +20 %; the other short-K layers are bound by shared-memory bandwidth, profiles/r1_step_breakdown_v5.md.)
 static inline void plan_epilogue(int avail, int stage_bytes, int force_single, int* epi_groups, int* stg_bufs) {
   if (!force_single && (avail - 4 * kStagingBytes) / stage_bytes >= 4) { *epi_groups = 2; *stg_bufs = 2; }
   else if (!force_single && (avail - 2 * kStagingBytes) / stage_bytes >= 5) { *epi_groups = 2; *stg_bufs = 1; }
   else if ((avail - 2 * kStagingBytes) / stage_bytes >= 4) { *epi_groups = 1; *stg_bufs = 2; }
   else { *epi_groups = 1; *stg_bufs = 1; }
-}
-
-__device__ __forceinline__ void column_sums(float (&v)[32], uint32_t lane) {
-  bfly<16>(v, lane);
-  bfly<8>(v, lane);
-  bfly<4>(v, lane);
-  bfly<2>(v, lane);
-  bfly<1>(v, lane);
 }
 
 // BatchNorm statistics of one staged output slab (128 pixel rows x 64 channels, bf16, SWIZZLE_128B rows of 128 B):
