@@ -31,6 +31,8 @@ struct K2Params {
   int pc;              // channels of P
   int TW, TH, tiles_w, tiles_h, pix_tiles;
   int MT, NT, G, splits;
+  int n_stages;        // TMA ring depth: kK2Stages, or fewer when a CTA has only 1-2 pixel tiles (then several CTAs share an
+                       // SM and overlap their start-up / epilogue latencies: projector dW has 24576 one-tile CTAs)
   int m_atoms;         // 1 (M = 64 duplicated to 128, or two kernel rows stacked when `stack`) or 2
   int paced;           // launched as clusters of G CTAs (the G kernel-column / tap groups of one pixel range): their TMA
                        // producers meet every kPace pixel tiles so the shared Q / P tiles are still in L2 for the others
@@ -44,7 +46,8 @@ struct K2Params {
 __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant__ K2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kK2Stages * kK2Stage);
+  const int n_stages = p.n_stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + n_stages * kK2Stage);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kK2Stages;
   uint64_t* tfull_bar = bars + 2 * kK2Stages;
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
                              : (acc_sets * p.n_cols <= 256) ? 256 : 512;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kK2Stages; ++i) {
+    for (int i = 0; i < n_stages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -99,8 +102,8 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
         const int rem = t - img * tiles_per_img;
         const int h0 = (rem / p.tiles_w) * p.TH;
         const int w0 = (rem % p.tiles_w) * p.TW;
-        const uint32_t st = it % kK2Stages;
-        const uint32_t ph = (it / kK2Stages) & 1;
+        const uint32_t st = it % n_stages;
+        const uint32_t ph = (it / n_stages) & 1;
         mbar_wait(&empty_bar[st], ph ^ 1);
         uint8_t* sQ = smem + st * kK2Stage;
         uint8_t* sP = sQ + 2 * kQAtom;
@@ -143,8 +146,8 @@ __global__ void __launch_bounds__(kK2Threads, 1) k2_kernel(const __grid_constant
     const int taps = acc_sets;
     uint32_t it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
-      const uint32_t st = it % kK2Stages;
-      const uint32_t ph = (it / kK2Stages) & 1;
+      const uint32_t st = it % n_stages;
+      const uint32_t ph = (it / n_stages) & 1;
       mbar_wait(&full_bar[st], ph);
       tc_fence_after();
       const uint32_t sQ = smem0 + st * kK2Stage;
@@ -386,12 +389,15 @@ static int run_k2(int mode, const void* q0, int qc0, const void* q1, int qc1, co
     attr_set = true;
   }
   const int grid = pl.MT * pl.NT * pl.G * pl.splits;
+  const int tiles_per_cta = ceil_div(pl.pix_tiles, pl.splits);
+  p.n_stages = (debug_knob(12) != 1 && tiles_per_cta < kK2Stages) ? tiles_per_cta : kK2Stages;
+  const int smem_bytes = p.n_stages * kK2Stage + 1024 + 512;
   p.paced = (pl.G > 1 && debug_knob(10) == 1) ? 1 : 0;   // A/B: see profiles/r1_k2_dram_traffic.md
   if (p.paced) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid, 1, 1);
     cfg.blockDim = dim3(kK2Threads, 1, 1);
-    cfg.dynamicSmemBytes = kK2Smem;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -402,7 +408,7 @@ static int run_k2(int mode, const void* q0, int qc0, const void* q1, int qc1, co
     cfg.numAttrs = 1;
     CMU_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k2_kernel, p));
   } else {
-    k2_kernel<<<grid, kK2Threads, kK2Smem, stream>>>(p);
+    k2_kernel<<<grid, kK2Threads, smem_bytes, stream>>>(p);
   }
   CMU_LAUNCH_CHECK();
   const int total = pl.G * pl.taps * qc * pc;

@@ -32,7 +32,8 @@ int cmu_debug_set(int key, int value);    /* 0: 1 = CUDA-core cross-check path f
                                              7: 1 = 64-wide layers on the 1-CTA kernel; 8: 1 = no kernel-row stacking in the
                                              64-channel wgrad; 9: 1 = one epilogue warp group; 10: 1 = wgrad CTAs of one
                                              pixel range launched as a paced cluster (A/B, profiles/r1_k2_dram_traffic.md);
-                                             11: 1 = ConvTranspose on the 1-CTA kernel (A/B) */
+                                             11: 1 = ConvTranspose on the 1-CTA kernel (A/B); 12: 1 = full-depth TMA ring for
+                                             one-tile wgrad CTAs (A/B) */
 
 /* ---- a1  patch-mask generator: CMU/backbones/UNet_encoder.py:106-139 (create_random_patch_mask) ------------
  * d_state: uint32[cmu_mask_state_words()] = MT19937 key[624] + position, same content as numpy's

@@ -64,6 +64,18 @@ def misc():
     w1 = torch.randn(64, 1, 3, 3, device=dev) * 0.3
     t5 = timeit(lambda: ops.conv3x3_c1_fprop(img, mask0, w1), flush)
     t6 = timeit(lambda: ops.conv3x3_c1_wgrad(img, mask0, a), flush)
+    dy = torch.randn(64, 1536, device=dev)
+    wfc = torch.randn(1536, S * S, device=dev) * 0.01
+    xin = torch.randn(64, S * S, device=dev)
+    from contrastive_masked_unet_b200 import functional as Fn
+    def lin():
+        xx = xin.clone().requires_grad_(True)
+        ww = wfc.requires_grad_(True)
+        ww.grad = None
+        y = Fn.LinearFn.apply(xx, ww, None)
+        y.backward(dy)
+    t7 = timeit(lin, flush)
+    print(f'projector fc0 fwd+bwd (64 x {S * S} -> 1536): {t7:.3f} ms', flush=True)
     print(f'conv_c1 fprop {t5:.3f} ms ({nb / t5 / 1e9:.2f} TB/s)  wgrad {t6:.3f} ms ({nb / t6 / 1e9:.2f} TB/s)', flush=True)
     print(f'head1x1 fwd {t1:.3f} ms ({(nb + dout.numel() * 4) / t1 / 1e9:.2f} TB/s)  bwd {t2:.3f} ms '
           f'({(2 * nb + dout.numel() * 4) / t2 / 1e9:.2f} TB/s)  transpose_cast {t3:.3f} ms ({6 * xb / t3 / 1e9:.2f} TB/s)  '
