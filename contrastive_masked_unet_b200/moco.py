@@ -175,6 +175,7 @@ class Moco_v2(nn.Module):
 
     def training_step(self, img_q, img_k):
         """moco2_module.py:287-309 without the Lightning plumbing: EMA of the key encoder, loss, dequeue/enqueue."""
+        ops._need_cuda(img_q, img_k)
         self._momentum_update_key_encoder()
         loss, k, _ = self.forward(img_q, img_k)
         self._dequeue_and_enqueue(k)

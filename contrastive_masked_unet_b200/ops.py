@@ -15,6 +15,9 @@ def _ptr(t):
 
 
 def _stream():
+    if not torch.cuda.is_available():
+        raise CmuError('contrastive_masked_unet_b200: no CUDA device -- this package runs on sm_100a only '
+                       '(there is no CPU fallback)')
     return torch.cuda.current_stream().cuda_stream
 
 

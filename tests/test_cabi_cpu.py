@@ -133,3 +133,38 @@ def test_checkpoint_handoff_pretrain_to_finetune(tmp_path):
     ou = O.OracleUNet()
     load_pretrained_into_unet(ou, path)
     assert torch.equal(ou.up_conv4.double_conv.double_conv[3].weight, m.pixel_decoder.up_conv4.double_conv.double_conv[3].weight)
+
+
+def test_host_planners_need_no_gpu():
+    """Workspace / grid planners are pure host code: callable without a device, positive and monotonic."""
+    L = C.lib
+    w1 = L.cmu_conv3x3_wgrad_workspace_bytes(64, 64, 64, 512, 512)
+    w2 = L.cmu_conv3x3_wgrad_workspace_bytes(512, 512, 64, 64, 64)
+    assert w1 >= 9 * 64 * 64 * 4 and w2 >= 9 * 512 * 512 * 4
+    assert L.cmu_convT2x2_wgrad_workspace_bytes(128, 64, 64, 256, 256) >= 4 * 128 * 64 * 4
+    assert L.cmu_sgemm_workspace_bytes(64, 256, 1536) % (64 * 256 * 4) == 0
+    assert L.cmu_sgemm_workspace_bytes(64, 256, 64) == 64 * 256 * 4                 # small K: no split
+    assert L.cmu_gemm_tn_workspace_bytes(64, 1536, 262144) >= 64 * 1536 * 4
+    assert L.cmu_soft_cldice_workspace_bytes(4, 256, 256) == (4 * 2 * 4 * 256 * 256 + 8) * 8
+    assert L.cmu_bn_bwd_grid() > 0 and L.cmu_conv_max_grid() > 0 and L.cmu_conv3x3_c1_grid() > 0
+
+
+def test_moco_constructor_matches_reference_rng_order_and_keys():
+    """Drop-in Moco_v2: same default-init weights and queue as the reference constructor under the same seed
+    (tests/golden/moco.json is minted from the unmodified reference), same buffers, encoder_k frozen; CPU input raises."""
+    g = json.load(open(os.path.join(GOLD, 'moco.json')))['case']
+    torch.manual_seed(g['seed'])
+    m = C.Moco_v2(emb_dim=1024, num_negatives=g['K'])
+    assert [k for k, _ in m.encoder_q.named_parameters()] == list(g['init_q'].keys())
+    for k, p in m.encoder_q.named_parameters():
+        assert float(p.detach().double().norm()) == pytest.approx(g['init_q'][k]['norm'], rel=1e-6)
+    assert float(m.queue.double().sum()) == pytest.approx(g['init_queue']['sum'], rel=1e-6, abs=1e-6)
+    assert set(dict(m.named_buffers())) >= {'queue', 'queue_ptr', 'val_queue', 'val_queue_ptr'}
+    assert tuple(m.queue.shape) == (1024, g['K']) and int(m.queue_ptr) == 0
+    assert all(not p.requires_grad for p in m.encoder_k.parameters())
+    assert all(p.requires_grad for p in m.encoder_q.parameters())
+    if not torch.cuda.is_available():
+        with pytest.raises(C.CmuError):
+            m.training_step(torch.rand(64, 32, 32), torch.rand(64, 32, 32))
+    with pytest.raises(NotImplementedError):
+        C.Moco_v2(use_mlp=True, num_negatives=64)
