@@ -14,8 +14,14 @@ def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
+_CUDA_OK = None
+
+
 def _stream():
-    if not torch.cuda.is_available():
+    global _CUDA_OK
+    if _CUDA_OK is None:
+        _CUDA_OK = torch.cuda.is_available()
+    if not _CUDA_OK:
         raise CmuError('contrastive_masked_unet_b200: no CUDA device -- this package runs on sm_100a only '
                        '(there is no CPU fallback)')
     return torch.cuda.current_stream().cuda_stream
