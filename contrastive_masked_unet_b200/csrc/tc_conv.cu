@@ -9,10 +9,11 @@
 // pixel).  conv3x3 loads, per 64-channel K chunk, THREE horizontally shifted (TH+2) x TW haloed patches (one per
 // kernel column s); the three kernel rows r are then plain 1024B-aligned row offsets of the same patch in the
 // UMMA shared-memory descriptor, so 3 TMA loads feed 9 taps (zero padding = TMA out-of-bounds fill).
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
-// warps 2..5 = epilogue (TMEM -> regs -> [bias] -> [per-channel sum / sum-of-squares for BatchNorm] -> bf16 ->
-// swizzled smem -> TMA store).  Accumulators are double buffered in TMEM so the epilogue of tile i overlaps the
-// MMAs of tile i+1.
+// Roles (320 threads): warp 0 = tile scheduler + TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
+// warps 2..5 (and 6..9 when shared memory allows a second staging ring: one warp group per TMEM accumulator) =
+// epilogue (TMEM -> regs -> [bias] -> bf16 -> the warp's own 32 rows of a swizzled staging slab -> the warp's own TMA
+// store; BatchNorm sum / sum-of-squares are taken from the staged bf16 slab).  Accumulators are double buffered in TMEM
+// so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "ptx.cuh"
 #include "k1_common.cuh"
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..5 [, 6..9])
     const uint32_t q = warp & 3;  // TMEM lane quadrant this warp may access
     const uint32_t row = q * 32 + lane;
     const int th = row >> p.tw_shift;

@@ -8,7 +8,7 @@
 // cores of the two SMs exchange the B halves, so per SM the shared-memory traffic per MMA drops to 4 KB (A) + 2-4 KB
 // (B half) for the same tensor cycles, and the weight tile is fetched from L2 once per pair instead of once per CTA.
 //
-// Structure per CTA = tc_conv.cu (TMA producer warp, MMA warp, 4 epilogue warps, double-buffered TMEM accumulators),
+// Structure per CTA = tc_conv.cu (TMA producer warp, MMA warp, 4 or 8 epilogue warps, double-buffered TMEM accumulators),
 // with the pair protocol of the PTX ISA:
 //   * both CTAs issue their TMA loads with .cta_group::2; the bytes are accounted on the LEADER's (rank 0) full barrier,
 //     which the leader arms with the byte count of both CTAs;
@@ -18,6 +18,8 @@
 //   * the epilogue warps of both CTAs hand an accumulator back by arriving (remotely for the peer) on the leader's
 //     tmem-empty barrier (count 8).
 // Tiles are assigned statically per cluster (both CTAs must walk the same tile sequence).
+// Also covered: ConvTranspose2d fprop (5-D scatter store) and dgrad (5-D .cta_group::2 gather); N = 64 tiles keep their
+// half of the weights resident in shared memory and stream activations only.
 #include "k1_common.cuh"
 #include "../../include/cmu_b200.h"
 
@@ -187,7 +189,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
+    // ------------------------------------------------------------------ epilogue (warps 2..5 [, 6..9], both CTAs)
     const uint32_t q = warp & 3;
     const uint32_t row = q * 32 + lane;
     const int th = row >> p.tw_shift;
