@@ -1,12 +1,19 @@
 // Seeded integer patch-mask generator, bit-exact with the reference's host code
 // (UNet_encoder.py:106-139 -> numpy legacy RandomState: MT19937 + masked-rejection Fisher-Yates shuffle).
 //
-// The random stream is inherently sequential (the number of 32-bit draws per shuffle is data dependent), so one
-// warp owns the stream: its 32 lanes regenerate the 624-word MT19937 state cooperatively (three dependent spans of
-// <= 227 words), lane 0 consumes tempered words through the rejection loop and performs the swaps in shared
-// memory.  The permutation prefixes (K masked patches per image) are written to global memory and a second,
-// grid-wide kernel rasterises them into the (B,S,S) uint8 mask with 16-byte stores.  Meant to run on a side
-// stream one step ahead of the training step.
+// The random stream is sequential (the number of 32-bit draws per Fisher-Yates step is data dependent), but the work
+// splits into two chains that need not run in lock-step:
+//   1. draw resolution (mask_draw_kernel, ONE warp): which word of the MT19937 stream does step i of which shuffle
+//      consume, and what index v_i does it yield?  The warp looks at 32 tempered words at a time.  Lane l's word is
+//      accepted iff (w_l & mask(i_l)) <= i_l with i_l = i - (#accepted among lanes < l): a recurrence over lanes that
+//      is solved by fixed-point iteration with ballots -- lane 0 is exact after the first pass and every pass fixes at
+//      least one more lane, in practice 2-3 passes resolve all 32 words (= ~23 Fisher-Yates steps).  The 624-word
+//      state is regenerated cooperatively (three dependent spans).  v_i goes to global memory as uint16.
+//   2. swap application (mask_apply_kernel, one THREAD per kept shuffle, shuffles are independent once the v_i are
+//      known): perm[i] <-> perm[v_i] for i = P-1..1 in shared memory, then the K-entry prefix is written out.
+// A grid-wide kernel rasterises the prefixes into the (B,S,S) uint8 mask with 16-byte stores.
+// 128 shuffles of arange(1024) (one B = 64 step: online + discarded target draws, quirk Q2): ~0.5 ms, down from 14 ms
+// for the round-1 kernel that walked the rejection loop and the swaps on one lane.
 //
 // Device state layout (uint32[625]): words [0,624) = MT19937 key, word 624 = position (624 = regenerate first),
 // identical to numpy's `get_state()[1:3]`, so a stream can be handed over from / to numpy.
@@ -61,61 +68,95 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
   return y;
 }
 
-// One warp.  n_shuffles consecutive shuffles of arange(P); for shuffle i < n_keep the first K entries of the
-// permutation are written to perm_prefix[i][K]; the remaining shuffles only advance the stream (quirk Q2: the
-// target encoder draws B shuffles although its mask is empty).
-__global__ void __launch_bounds__(32) mask_shuffle_kernel(uint32_t* state, int* __restrict__ perm_prefix, int P, int K,
-                                                          int n_shuffles, int n_keep) {
-  extern __shared__ uint32_t sm[];
-  uint32_t* mt = sm;                              // [624]
-  int* perm = reinterpret_cast<int*>(sm + MT_N);  // [P]
-  __shared__ int s_need_regen;
+// Chain 1.  One warp; n_shuffles consecutive shuffles of arange(P).  For shuffle sh < n_keep the accepted index of
+// step i is written to vs[sh][i]; the remaining shuffles only advance the stream (quirk Q2: the target encoder draws
+// B shuffles although its mask is empty).
+__global__ void __launch_bounds__(32) mask_draw_kernel(uint32_t* state, uint16_t* __restrict__ vs, int P, int n_shuffles,
+                                                       int n_keep) {
+  __shared__ uint32_t mt[MT_N];
   const uint32_t lane = threadIdx.x;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   for (int i = lane; i < MT_N; i += 32) mt[i] = state[i];
-  int pos = (int)state[MT_N];
+  int pos = (int)state[MT_N];   // warp-uniform
   __syncwarp();
   for (int sh = 0; sh < n_shuffles; ++sh) {
     const bool keep = sh < n_keep;
-    if (keep) {
-      for (int i = lane; i < P; i += 32) perm[i] = i;
-    }
-    __syncwarp();
-    int i = P - 1;
-    // lane 0 consumes words until the state block is exhausted, then the warp regenerates and lane 0 resumes
-    while (true) {
-      if (lane == 0) {
-        s_need_regen = 0;
-        while (i >= 1) {
-          uint32_t mask = (uint32_t)i;
-          mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
-          if (pos >= MT_N) { s_need_regen = 1; break; }
-          const uint32_t v = mt_temper(mt[pos++]) & mask;
-          if (v <= (uint32_t)i) {
-            if (keep) {
-              const int t = perm[i];
-              perm[i] = perm[v];
-              perm[v] = t;
-            }
-            --i;
-          }
-        }
+    uint16_t* v = vs + (size_t)sh * P;
+    int i = P - 1;              // warp-uniform: the Fisher-Yates step the next accepted word serves
+    while (i >= 1) {
+      if (pos >= MT_N) {
+        mt_regen(mt, lane);
+        pos = 0;
       }
-      __syncwarp();
-      const int need = s_need_regen;
-      __syncwarp();
-      if (!need) break;
-      mt_regen(mt, lane);
-      pos = 0;
-      i = __shfl_sync(0xffffffffu, i, 0);
+      const int idx = pos + (int)lane;
+      const bool valid = idx < MT_N;
+      const uint32_t w = valid ? mt_temper(mt[idx]) : 0u;
+      // fixed point of: ok_l = valid_l && i_l >= 1 && (w_l & mask(i_l)) <= i_l,  i_l = i - popc(ok & lanes < l)
+      int a = 0, il = i;
+      uint32_t x = 0, acc = 0, prev = 0;
+      bool first = true;
+      while (true) {
+        il = i - a;
+        const uint32_t m = il >= 1 ? (0xffffffffu >> __clz(il)) : 0u;   // smallest 2^k - 1 >= il (rk_interval)
+        x = w & m;
+        const bool ok = valid && il >= 1 && x <= (uint32_t)il;
+        acc = __ballot_sync(0xffffffffu, ok);
+        a = __popc(acc & lt_mask);
+        if (!first && acc == prev) break;
+        prev = acc;
+        first = false;
+      }
+      const bool mine = (acc >> lane) & 1u;
+      if (mine && keep) v[il] = (uint16_t)x;
+      // the shuffle ends at the lane that served step 1: words behind it belong to the next shuffle
+      const uint32_t fin = __ballot_sync(0xffffffffu, mine && il == 1);
+      const int nvalid = (MT_N - pos) < 32 ? (MT_N - pos) : 32;
+      pos += fin ? __ffs((int)fin) : nvalid;
+      i -= __popc(acc);
     }
-    pos = __shfl_sync(0xffffffffu, pos, 0);
-    if (keep) {
-      for (int k = lane; k < K; k += 32) perm_prefix[(size_t)sh * K + k] = perm[k];
-    }
-    __syncwarp();
   }
+  __syncwarp();
   for (int i = lane; i < MT_N; i += 32) state[i] = mt[i];
   if (lane == 0) state[MT_N] = (uint32_t)pos;
+}
+
+// Chain 2.  Thread t of block b applies the swaps of shuffle b*T + t to its own column of perm[P][T] (uint16, shared
+// memory) and writes the first K entries of the permutation.
+__global__ void mask_apply_kernel(const uint16_t* __restrict__ vs, int* __restrict__ perm_prefix, int P, int K,
+                                  int n_keep, int T) {
+  extern __shared__ uint16_t perm[];
+  const int t = threadIdx.x;
+  const int sh = blockIdx.x * T + t;
+  if (sh >= n_keep) return;
+  for (int i = 0; i < P; ++i) perm[i * T + t] = (uint16_t)i;
+  const uint16_t* v = vs + (size_t)sh * P;
+  constexpr int kChunk = 16;
+  uint16_t cur[kChunk], nxt[kChunk];
+#pragma unroll
+  for (int u = 0; u < kChunk; ++u) {
+    const int i = P - 1 - u;
+    cur[u] = i >= 1 ? v[i] : (uint16_t)0;
+  }
+  for (int base = P - 1; base >= 1; base -= kChunk) {
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) {   // indices of the next chunk are in flight while this one is applied
+      const int i = base - kChunk - u;
+      nxt[u] = i >= 1 ? v[i] : (uint16_t)0;
+    }
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) {
+      const int i = base - u;
+      if (i >= 1) {
+        const int j = cur[u];
+        const uint16_t pi = perm[i * T + t];
+        perm[i * T + t] = perm[j * T + t];
+        perm[j * T + t] = pi;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) cur[u] = nxt[u];
+  }
+  for (int k = 0; k < K; ++k) perm_prefix[(size_t)sh * K + k] = perm[k * T + t];
 }
 
 // mask[b, r*ps .. , c*ps ..] = 1 for the K selected patches; the buffer must be zero-filled by `mask_clear`.
@@ -158,24 +199,42 @@ int cmu_mask_seed(unsigned int* d_state, unsigned int seed, void* stream) {
   return 0;
 }
 
+// Workspace of cmu_mask_generate: int32 perm_prefix[batch][K] followed by uint16 vs[batch][P] (16-byte aligned parts).
+long long cmu_mask_workspace_bytes(int batch, int n_patches, int k_masked) {
+  const long long a = (((long long)batch * k_masked * 4) + 15) & ~15LL;
+  const long long b = (((long long)batch * n_patches * 2) + 15) & ~15LL;
+  return a + b + 16;
+}
+
 // Advances the stream by `n_shuffles` shuffles of arange((S/ps)^2); the first `batch` of them define `mask`.
-// perm_ws: int32[batch * K] workspace, K = masked patches per image (0 -> mask stays all-zero).
+// perm_ws: cmu_mask_workspace_bytes(batch, P, K) bytes, K = masked patches per image (0 -> mask stays all-zero);
+// mask may be NULL (the stream only advances).
 int cmu_mask_generate(unsigned int* d_state, unsigned char* mask, int* perm_ws, int batch, int img_size, int patch_size,
                       int k_masked, int n_shuffles, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  CMU_REQUIRE(img_size % patch_size == 0, "mask: img_size %% patch_size != 0");
+  CMU_REQUIRE(patch_size > 0 && img_size % patch_size == 0, "mask: img_size %% patch_size != 0");
   const int g = img_size / patch_size;
   const int P = g * g;
+  CMU_REQUIRE(P <= 65536, "mask: too many patches (%d)", P);
   CMU_REQUIRE(k_masked >= 0 && k_masked <= P, "mask: bad K");
   CMU_REQUIRE(n_shuffles >= 0 && batch >= 0, "mask: bad counts");
-  const size_t shmem = (MT_N + (size_t)P) * 4;
-  CMU_REQUIRE(shmem <= 200 * 1024, "mask: too many patches (%d)", P);
   const int n_keep = (k_masked > 0 && mask != nullptr) ? (batch < n_shuffles ? batch : n_shuffles) : 0;
-  if (shmem > 48 * 1024) {
-    CMU_CHECK_CUDA(cudaFuncSetAttribute(mask_shuffle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-  }
+  CMU_REQUIRE(n_keep == 0 || perm_ws != nullptr, "mask: workspace missing");
+  int* perm_prefix = perm_ws;
+  uint16_t* vs = perm_ws == nullptr ? nullptr : reinterpret_cast<uint16_t*>(
+      reinterpret_cast<uint8_t*>(perm_ws) + ((((size_t)batch * k_masked * 4) + 15) & ~(size_t)15));
   if (n_shuffles > 0) {
-    mask_shuffle_kernel<<<1, 32, shmem, st>>>(d_state, perm_ws, P, k_masked, n_shuffles, n_keep);
+    mask_draw_kernel<<<1, 32, 0, st>>>(d_state, vs, P, n_shuffles, n_keep);
+    CMU_LAUNCH_CHECK();
+  }
+  if (n_keep > 0) {
+    int T = 32;
+    while (T > 1 && (size_t)P * T * 2 > 160 * 1024) T >>= 1;
+    const size_t shmem = (size_t)P * T * 2;
+    if (shmem > 48 * 1024) {
+      CMU_CHECK_CUDA(cudaFuncSetAttribute(mask_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    }
+    mask_apply_kernel<<<(n_keep + T - 1) / T, T, shmem, st>>>(vs, perm_prefix, P, k_masked, n_keep, T);
     CMU_LAUNCH_CHECK();
   }
   if (mask != nullptr) {
@@ -186,7 +245,7 @@ int cmu_mask_generate(unsigned int* d_state, unsigned char* mask, int* perm_ws, 
       const size_t total = (size_t)n_keep * k_masked * patch_size * (patch_size % 16 == 0 ? patch_size / 16 : patch_size);
       size_t blocks = (total + 255) / 256;
       if (blocks > (size_t)num_sms() * 8) blocks = (size_t)num_sms() * 8;
-      mask_raster_kernel<<<(int)blocks, 256, 0, st>>>(perm_ws, mask, n_keep, img_size, patch_size, k_masked);
+      mask_raster_kernel<<<(int)blocks, 256, 0, st>>>(perm_prefix, mask, n_keep, img_size, patch_size, k_masked);
       CMU_LAUNCH_CHECK();
     }
   }

@@ -42,6 +42,15 @@ class BNConfig:
         self.grad = torch.is_grad_enabled()     # captured at call time (grad mode is always off inside Function.forward)
 
 
+def _conv_bias_grad(dy, bn_training):
+    """Gradient of the conv bias in front of a BatchNorm: analytically zero under batch statistics (the mean removes any
+    per-channel constant); with frozen / eval-mode statistics it is the per-channel sum of dy."""
+    n, h, w, c = dy.shape
+    if bn_training:
+        return torch.zeros(c, dtype=torch.float32, device=dy.device)
+    return ops.colsum_bf16(n * h * w, c, dy)
+
+
 class ConvBNReLUFn(torch.autograd.Function):
     """Conv3x3(pad 1) -> BatchNorm2d -> ReLU [-> MaxPool2d(2)] on (x0 | x1) (channel concat, x1 optional).
     UNet_encoder.py:18-30,44-49 / munet_neck.py:48-49."""
@@ -81,7 +90,7 @@ class ConvBNReLUFn(torch.autograd.Function):
             dx0 = _nchw_view(g0) if ctx.needs_input_grad[0] else None
             dx1 = _nchw_view(g1) if (g1 is not None and ctx.needs_input_grad[1]) else None
         dw = ops.conv3x3_wgrad(a0, a1, dy) if ctx.needs_input_grad[2] else None
-        dbias = torch.zeros(dy.shape[3], dtype=torch.float32, device=dy.device) if ctx.needs_input_grad[3] else None
+        dbias = _conv_bias_grad(dy, ctx.bn_training) if ctx.needs_input_grad[3] else None
         return dx0, dx1, dw, dbias, dgamma, dbeta, None, None, None
 
 
@@ -107,7 +116,7 @@ class FirstConvBNReLUFn(torch.autograd.Function):
         da = _nhwc(to_act(d_act))
         dy, dgamma, dbeta = ops.bn_relu_bwd(da, None, y, scale, shift, mean, rstd, ctx.bn_training)
         dw = ops.conv3x3_c1_wgrad(x, mask, dy) if ctx.needs_input_grad[2] else None
-        dbias = torch.zeros(dy.shape[3], dtype=torch.float32, device=dy.device) if ctx.needs_input_grad[3] else None
+        dbias = _conv_bias_grad(dy, ctx.bn_training) if ctx.needs_input_grad[3] else None
         # the input image never needs a gradient on this path (f1 "not needed")
         return None, None, dw, dbias, dgamma, dbeta, None, None, None
 

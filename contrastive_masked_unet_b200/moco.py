@@ -12,6 +12,7 @@ import torch.nn as nn
 from . import functional as Fn
 from . import ops
 from ._lib import CmuError, lib
+from .functional import _world
 from .modules import DoubleConv, DownBlock, concat_all_gather, register
 
 BF16 = torch.bfloat16
@@ -128,13 +129,22 @@ class Moco_v2(nn.Module):
         self.register_buffer('val_queue_ptr', torch.zeros(1, dtype=torch.long))
         self._rows = None            # bf16 (K, D) working copy of `queue` (one negative per row)
         self._ptr = 0
+        self._sig = None
+        self.shuffle_bn = True       # batch shuffle across ranks whenever a process group with world > 1 is active
         self._ema_table = None
 
     # ------------------------------------------------------------------ queue
+    def _queue_sig(self):
+        # in-place writes (load_state_dict's copy_, user code) bump the version counters; no device sync involved
+        return (self.queue.data_ptr(), self.queue._version, self.queue_ptr._version)
+
     def _queue_rows(self):
-        if self._rows is None or self._rows.device != self.queue.device:
+        """bf16 (K, D) working copy of `queue` + host copy of `queue_ptr`, rebuilt whenever the buffers were written by
+        anything but this module's own enqueue (checkpoint resume, `.to()`, code written against the reference API)."""
+        if self._rows is None or self._rows.device != self.queue.device or self._sig != self._queue_sig():
             self._rows = self.queue.t().contiguous().to(BF16)
             self._ptr = int(self.queue_ptr)
+            self._sig = self._queue_sig()
         return self._rows
 
     @torch.no_grad()
@@ -148,6 +158,31 @@ class Moco_v2(nn.Module):
         lib.cmu_queue_enqueue(keys.data_ptr(), n, d, kneg, self._ptr, rows.data_ptr(), self.queue.data_ptr(), ops._stream())
         self._ptr = (self._ptr + n) % kneg
         self.queue_ptr[0] = self._ptr
+        self._sig = self._queue_sig()        # our own writes (raw-pointer kernel + the pointer store) keep the cache valid
+
+    # ------------------------------------------------------------------ shuffle-BN (moco2_module.py:177-222)
+    @torch.no_grad()
+    def _batch_shuffle_ddp(self, x):
+        """All-gather the key images, draw ONE permutation on rank 0 (CPU torch RNG, like `torch.randperm(n).cuda()` in
+        the reference), broadcast it, and keep this rank's slice: the per-GPU BatchNorm of `encoder_k` then sees a
+        different sample set than `encoder_q` (the information leak the shuffle exists to prevent)."""
+        import torch.distributed as dist
+        n_this = x.shape[0]
+        x_all = concat_all_gather(x.contiguous())
+        n_all = x_all.shape[0]
+        idx_shuffle = torch.randperm(n_all).to(x.device)
+        dist.broadcast(idx_shuffle, src=0)
+        idx_unshuffle = torch.argsort(idx_shuffle)
+        idx_this = idx_shuffle.view(n_all // n_this, -1)[dist.get_rank()]
+        return x_all[idx_this], idx_unshuffle
+
+    @torch.no_grad()
+    def _batch_unshuffle_ddp(self, x, idx_unshuffle):
+        import torch.distributed as dist
+        n_this = x.shape[0]
+        x_all = concat_all_gather(x.contiguous())
+        idx_this = idx_unshuffle.view(x_all.shape[0] // n_this, -1)[dist.get_rank()]
+        return x_all[idx_this]
 
     @torch.no_grad()
     def _momentum_update_key_encoder(self):
@@ -169,7 +204,12 @@ class Moco_v2(nn.Module):
         ops._need_cuda(img_q, img_k)
         q = self.encoder_q(img_q)
         with torch.no_grad():
+            shuffle = self.shuffle_bn and _world() > 1            # moco2_module.py:246-255 (`_use_ddp_or_ddp2`)
+            if shuffle:
+                img_k, idx_unshuffle = self._batch_shuffle_ddp(img_k)
             k = ops.l2_normalize_rows(self.encoder_k(img_k).contiguous().float())
+            if shuffle:
+                k = self._batch_unshuffle_ddp(k, idx_unshuffle)
         loss = MocoLossFn.apply(q, k, self._queue_rows(), self.hparams['softmax_temperature'])
         return loss, k, q
 
@@ -184,5 +224,6 @@ class Moco_v2(nn.Module):
     def __getstate__(self):
         d = dict(self.__dict__)
         d['_rows'] = None
+        d['_sig'] = None
         d['_ema_table'] = None
         return d

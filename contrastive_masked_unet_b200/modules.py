@@ -44,58 +44,76 @@ class MaskStream:
 
     pair_mode (set by CM_UNet): the stream is inherently sequential, so after the (online, target) pair of step t has
     been served the pair of step t+1 is generated on a side CUDA stream while step t computes -- same draws, same
-    order, off the critical path.  A changed batch/size rolls the state back and regenerates synchronously."""
+    order, off the critical path.  The prefetch is speculative and always reversible: the state is snapshotted before
+    the pair (`backup`) and between its halves (`mid`), so a call sequence that is not online -> target (a changed
+    batch / size, `extract_feat` / mode='tensor' calls without a target call, `get_numpy_state`) rolls the stream back
+    to its logical position and continues exactly where numpy would be."""
 
     def __init__(self):
         self.state = None
         self.pair_mode = False
-        self._pref = None            # (key, mask, event, state_backup)
-        self._target_served = None   # key of a prefetched pair whose target half is still to be "drawn"
+        self._pref = None            # (key, mask, event, backup, mid): a prefetched pair nobody has consumed yet
+        self._target_owed = None     # (tkey, mid): online half consumed, its target half already drawn speculatively
         self._side = None
+        self._last_key = None
 
     def _ensure(self, device):
         if self.state is None:
             self.set_numpy_state(np.random.get_state(), device)
         elif self.state.device != device:
+            self._settle()
             self.state = self.state.to(device)
 
     def seed(self, seed, device='cuda'):
-        self._drop_prefetch()
+        self._pref = self._target_owed = None     # a new seed discards any speculation (after the side stream is done)
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
         self.state = torch.empty(lib.cmu_mask_state_words(), dtype=torch.int32, device=device)
         lib.cmu_mask_seed(self.state.data_ptr(), int(seed) & 0xFFFFFFFF, ops._stream())
 
     def set_numpy_state(self, np_state, device='cuda'):
         assert np_state[0] == 'MT19937'
-        self._drop_prefetch()
+        self._pref = self._target_owed = None
+        if self._side is not None and torch.cuda.is_available():
+            torch.cuda.current_stream().wait_stream(self._side)
         words = np.concatenate([np.asarray(np_state[1], dtype=np.uint32), np.array([np_state[2]], dtype=np.uint32)])
         self.state = torch.from_numpy(words.view(np.int32).copy()).to(device)
 
     def get_numpy_state(self):
-        """Logical position of the stream (a prefetched, not yet consumed pair does not count)."""
+        """Logical position of the stream (speculatively drawn shuffles do not count)."""
         st = self.state
         if self._pref is not None:
             self._pref[2].synchronize()
             st = self._pref[3]
+        elif self._target_owed is not None:
+            st = self._target_owed[1]
         w = st.cpu().numpy().view(np.uint32)
         return ('MT19937', w[:624].copy(), int(w[624]), 0, 0.0)
 
-    def _drop_prefetch(self):
+    def _settle(self):
+        """Roll the device state back to the logical stream position (undo whatever was drawn speculatively)."""
         if self._pref is not None:
-            _, _, ev, backup = self._pref
+            _, _, ev, backup, _ = self._pref
             torch.cuda.current_stream().wait_event(ev)
-            self.state.copy_(backup)          # roll the stream back to its logical position
+            self.state.copy_(backup)
             self._pref = None
-        self._target_served = None
+        elif self._target_owed is not None:
+            self.state.copy_(self._target_owed[1])        # keep the online half, undo the target half
+        self._target_owed = None
+
+    _drop_prefetch = _settle
 
     @staticmethod
     def _k(img_size, patch_size, mask_ratio):
         g = img_size // patch_size
         return min(int(mask_ratio * img_size * img_size) // (patch_size * patch_size), g * g)
 
-    def _launch(self, batch, img_size, patch_size, k, n_shuffles, device):
-        mask = torch.empty(batch, img_size, img_size, dtype=torch.uint8, device=device)
-        ws = torch.empty(max(batch * k, 1), dtype=torch.int32, device=device)
-        lib.cmu_mask_generate(self.state.data_ptr(), mask.data_ptr(), ws.data_ptr(), batch, img_size, patch_size, k,
+    def _launch(self, batch, img_size, patch_size, k, n_shuffles, device, want_mask=True):
+        mask = torch.empty(batch, img_size, img_size, dtype=torch.uint8, device=device) if want_mask else None
+        g = img_size // patch_size
+        nbytes = lib.cmu_mask_workspace_bytes(batch, g * g, k)
+        ws = torch.empty(max(nbytes // 4, 1), dtype=torch.int32, device=device)
+        lib.cmu_mask_generate(self.state.data_ptr(), ops._ptr(mask), ws.data_ptr(), batch, img_size, patch_size, k,
                               n_shuffles, ops._stream())
         return mask
 
@@ -106,51 +124,56 @@ class MaskStream:
         self._side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self._side):
             backup = self.state.clone()
-            mask = self._launch(batch, img_size, patch_size, k, 2 * batch, device)   # online half kept + target draws
+            mask = self._launch(batch, img_size, patch_size, k, batch, device)                    # online half
+            mid = self.state.clone()
+            self._launch(batch, img_size, patch_size, 0, batch, device, want_mask=False)          # target draws (Q2)
             ev = torch.cuda.Event()
             ev.record(self._side)
-        self._pref = (key, mask, ev, backup)
+        self._pref = (key, mask, ev, backup, mid)
 
     def generate(self, batch, img_size, patch_size, mask_ratio, device):
         """One `create_random_patch_mask` call: consumes `batch` shuffles, returns ((B,S,S) uint8 mask, K)."""
         self._ensure(device)
         k = self._k(img_size, patch_size, mask_ratio)
         if not self.pair_mode:
+            self._settle()
             return self._launch(batch, img_size, patch_size, k, batch, device), k
         if k > 0:                                             # online call
             key = (batch, img_size, patch_size, k)
+            self._last_key = key
+            if self._target_owed is not None:                 # previous online call was not followed by its target call
+                self._settle()
             if self._pref is not None and self._pref[0] == key:
-                _, mask, ev, _ = self._pref
+                _, mask, ev, _, mid = self._pref
                 cur = torch.cuda.current_stream()
                 cur.wait_event(ev)
                 mask.record_stream(cur)
                 self._pref = None
-                self._target_served = key[:3]
-                self._last_key = key
+                self._target_owed = (key[:3], mid)
                 return mask, k
-            self._drop_prefetch()
-            self._last_key = key
+            self._settle()
             return self._launch(batch, img_size, patch_size, k, batch, device), k
         # target call (mask_ratio 0): B shuffles are drawn and discarded (Q2)
         tkey = (batch, img_size, patch_size)
-        if self._target_served == tkey:
-            self._target_served = None                        # already drawn by the prefetched pair
+        if self._target_owed is not None and self._target_owed[0] == tkey:
+            self._target_owed = None                          # already drawn by the prefetched pair
             mask = torch.zeros(batch, img_size, img_size, dtype=torch.uint8, device=device)
         else:
-            self._drop_prefetch()
+            self._settle()
             mask = self._launch(batch, img_size, patch_size, 0, batch, device)
         nxt = self._last_key
         if nxt is not None and nxt[:3] == tkey:
             self._prefetch(nxt, device)                       # pair of the next step, on the side stream
         return mask, 0
 
-    _last_key = None
-
     def __getstate__(self):
         d = dict(self.__dict__)
         if d.get('_pref') is not None:
+            d['_pref'][2].synchronize()
             d['state'] = d['_pref'][3]
-        d['_pref'] = d['_side'] = d['_target_served'] = None
+        elif d.get('_target_owed') is not None:
+            d['state'] = d['_target_owed'][1]
+        d['_pref'] = d['_side'] = d['_target_owed'] = None
         return d
 
 
@@ -601,11 +624,28 @@ def cmunet_config(img_size=224, patch_size=16, mask_ratio=0.65):
 
 
 def try_register_mmengine():
-    """Registers the drop-in classes under the reference's registry names when mmengine is importable."""
+    """Registers the drop-in classes under the reference's registry names, replacing the reference's own entries.
+
+    The reference builds its model with `cmae.registry.MODELS.build(cfg.model)` (cmae/models/builder.py:12-14); that
+    registry is a CHILD of mmengine's root `MODELS` (cmae/registry.py:83-84) and a child's own entries shadow the
+    parent's, so the swap has to happen in the child: `import cmae.models` first (the reference classes register
+    themselves on import, without `force`), then `register_module(name=..., module=cls, force=True)` there.  mmengine's
+    root registry gets the same entries for code that builds through `mmengine.registry.MODELS` directly.
+    Returns the list of registries written (empty = neither `cmae` nor `mmengine` is importable)."""
+    done = []
+    try:
+        import cmae.models  # noqa: F401  (must precede the forced registration)
+        from cmae.registry import MODELS as CM
+        for name, cls in MODELS.items():
+            CM.register_module(name=name, module=cls, force=True)
+        done.append('cmae.registry.MODELS')
+    except ImportError:
+        pass
     try:
         from mmengine.registry import MODELS as MM
-    except Exception:
-        return False
-    for name, cls in MODELS.items():
-        MM.register_module(name=name, module=cls, force=True)
-    return True
+        for name, cls in MODELS.items():
+            MM.register_module(name=name, module=cls, force=True)
+        done.append('mmengine.registry.MODELS')
+    except ImportError:
+        pass
+    return done

@@ -40,7 +40,9 @@ int cmu_debug_set(int key, int value);    /* 0: 1 = CUDA-core cross-check path f
  * np.random.get_state()[1:3] (legacy global RNG used at UNet_encoder.py:124).  Bit-exact with the reference. */
 int cmu_mask_state_words(void);
 int cmu_mask_seed(unsigned int* d_state, unsigned int seed, void* stream);             /* == np.random.seed(seed) */
-int cmu_mask_generate(unsigned int* d_state, unsigned char* mask /* (batch,S,S) u8 or NULL */, int* perm_ws /* int32[batch*K] */,
+long long cmu_mask_workspace_bytes(int batch, int n_patches, int k_masked);            /* host-only planner */
+int cmu_mask_generate(unsigned int* d_state, unsigned char* mask /* (batch,S,S) u8 or NULL: only advance the stream */,
+                      int* perm_ws /* cmu_mask_workspace_bytes(batch, (S/ps)^2, K) bytes */,
                       int batch, int img_size, int patch_size, int k_masked, int n_shuffles, void* stream);
 
 /* ---- a2/a3  DoubleConv pieces: CMU/backbones/UNet_encoder.py:18-30,141-158 == FT/model.py:16-26 ----------- */
@@ -162,6 +164,16 @@ int cmu_queue_enqueue(const float* keys, int n, int d, int k, int ptr, void* que
 int cmu_ema_chunks(const long long* d_table /* [n][3] = dst, src, count */, int n_chunks, float momentum, void* stream);
 int cmu_adamw_chunks(const long long* d_table /* [n][6] = p, g, m, v, count, decay */, int n_chunks, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* dynamic loss scaling of mmengine's AmpOptimWrapper(loss_scale='dynamic') (cmunet_config.py:76-78 == torch.amp.GradScaler):
+ * d_amp = int32[5] device state {float scale, int found_inf, int optimizer steps taken, int growth tracker, float 1/scale
+ * of the current gradients}.  cmu_adamw_chunks_amp = found-inf reduction over all gradients + scale update + AdamW that
+ * unscales the gradients and leaves parameters and moments untouched after an overflow; no host synchronisation. */
+int cmu_amp_init(int* d_amp, float init_scale, void* stream);
+int cmu_adamw_chunks_amp(const long long* d_table, int n_chunks, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, int* d_amp, float growth, float backoff, int growth_interval, void* stream);
+/* SGD with momentum (torch.optim.SGD semantics; MoCo-v2 optimizer, MOCO/moco2_module.py configure_optimizers) */
+int cmu_sgd_chunks(const long long* d_table /* [n][4] = p, g, momentum buffer, count */, int n_chunks, float lr,
+                   float momentum, float weight_decay, int first_step, void* stream);
 
 /* ---- a15  fine-tuning losses: FT/metrics.py:135-220,503-504 ----------------------------------------------- */
 int cmu_seg_losses(const float* logits, const double* gt, double* acc /* double[4] */, double* out /* dice, iou, ce */,

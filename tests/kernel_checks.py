@@ -334,7 +334,7 @@ def check_mask(seed=60, b=6, s=128, ps=16, ratio=0.65, steps=2):
     bad = 0
     for _ in range(steps):
         mask = torch.empty(b, s, s, dtype=torch.uint8, device=DEV)
-        ws = torch.empty(max(b * k, 1), dtype=torch.int32, device=DEV)
+        ws = torch.empty(max(lib.cmu_mask_workspace_bytes(b, p, k) // 4, 1), dtype=torch.int32, device=DEV)
         lib.cmu_mask_generate(st.data_ptr(), mask.data_ptr(), ws.data_ptr(), b, s, ps, k, b, stream)
         lib.cmu_mask_generate(st.data_ptr(), 0, 0, b, s, ps, 0, b, stream)      # target encoder: draws only (Q2)
         ref, _ = patch_mask(rng, b, s, ps, ratio)
@@ -379,6 +379,95 @@ def check_mask_pair_mode(seed=60, b=5, s=96, steps=4):
     res = {'mismatch_bytes': bad, 'logical_stream_ok': ok, 'prefetch_outstanding': ms._pref is not None}
     assert bad == 0 and ok, res
     return res
+
+
+def check_mask_interleaved_calls(seed=62, b=4, s=96):
+    """Speculative pair prefetch stays bit-exact with numpy's order for call sequences that are NOT online -> target:
+    mode='tensor' style online-only calls after a training step, get_numpy_state in between, a size change, pickling
+    (the prefetched target half must be rolled back when no target call follows)."""
+    import pickle
+    import contrastive_masked_unet_b200 as C
+    from oracle.mask_oracle import MT19937, patch_mask
+    ms = C.MaskStream()
+    ms.pair_mode = True
+    ms.seed(seed, DEV)
+    rng = MT19937(seed)
+    dev = torch.device(DEV)
+    bad = 0
+    ok = True
+
+    def online(bb, ss):
+        nonlocal bad
+        m, _ = ms.generate(bb, ss, 16, 0.65, dev)
+        ref, _ = patch_mask(rng, bb, ss, 16, 0.65)
+        torch.cuda.synchronize()
+        bad += int((m.cpu().numpy() != ref).sum())
+
+    def target(bb, ss):
+        nonlocal bad
+        m, _ = ms.generate(bb, ss, 16, 0.0, dev)
+        patch_mask(rng, bb, ss, 16, 0.0)
+        bad += int(m.sum())
+
+    def position_ok():
+        st = ms.get_numpy_state()
+        r2 = MT19937()
+        r2.set_state(st[1], st[2])
+        key, pos = rng.get_state()
+        r3 = MT19937()
+        r3.set_state(key, pos)
+        return [r2.next_u32() for _ in range(3)] == [r3.next_u32() for _ in range(3)]
+
+    online(b, s); target(b, s)            # training step -> pair of the next step is prefetched
+    online(b, s)                          # extract_feat: consumes the prefetched online half, no target call follows
+    ok &= position_ok()                   # logical position = +B, although +2B were drawn speculatively
+    online(b, s)                          # second extract_feat: must start at +B (roll back the speculative target half)
+    ok &= position_ok()
+    online(b, s); target(b, s)            # training resumes
+    online(b, s); target(b, s)
+    ms2 = pickle.loads(pickle.dumps(ms))  # pickled at a point where a prefetched pair is outstanding
+    ok &= position_ok()
+    online(b + 1, s); target(b + 1, s)    # batch change drops the prefetch
+    online(b + 1, s)
+    ms.pair_mode = False
+    online(b, s + 32)                     # plain mode after an owed target half
+    ok &= position_ok()
+    # the unpickled copy continues from the logical position it was saved at
+    rng2 = MT19937(seed)
+    for _ in range(4):
+        patch_mask(rng2, b, s, 16, 0.65)
+    for _ in range(3):
+        patch_mask(rng2, b, s, 16, 0.0)
+    # (sequence so far: on,tg,on,on,on,tg,on,tg = 5 online + 3 target calls of batch b)
+    patch_mask(rng2, b, s, 16, 0.65)
+    m2, _ = ms2.generate(b, s, 16, 0.65, dev)
+    ref2, _ = patch_mask(rng2, b, s, 16, 0.65)
+    torch.cuda.synchronize()
+    bad2 = int((m2.cpu().numpy() != ref2).sum())
+    res = {'mismatch_bytes': bad, 'positions_ok': bool(ok), 'unpickled_mismatch': bad2}
+    assert bad == 0 and ok and bad2 == 0, res
+    return res
+
+
+def time_mask(b=64, s=512, reps=5):
+    """ms per training-step pair (B online + B discarded target shuffles) of the mask generator."""
+    st = torch.zeros(lib.cmu_mask_state_words(), dtype=torch.int32, device=DEV)
+    stream = torch.cuda.current_stream().cuda_stream
+    lib.cmu_mask_seed(st.data_ptr(), 60, stream)
+    p = (s // 16) ** 2
+    k = int(0.65 * s * s) // 256
+    mask = torch.empty(b, s, s, dtype=torch.uint8, device=DEV)
+    ws = torch.empty(lib.cmu_mask_workspace_bytes(b, p, k) // 4, dtype=torch.int32, device=DEV)
+    ts = []
+    for _ in range(reps + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib.cmu_mask_generate(st.data_ptr(), mask.data_ptr(), ws.data_ptr(), b, s, 16, k, b, stream)
+        lib.cmu_mask_generate(st.data_ptr(), 0, 0, b, s, 16, 0, b, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return {'ms_per_pair': sorted(ts[2:])[len(ts[2:]) // 2], 'B': b, 'S': s}
 
 
 # ------------------------------------------------------------------------------------------------ linear / BN1d / optim
@@ -582,6 +671,62 @@ def check_optim(seed=11):
     return res
 
 
+def check_optim_amp(seed=12):
+    """FusedAdamW + DynamicLossScaler against torch.optim.AdamW + torch.amp.GradScaler over 6 steps with an overflow
+    injected at step 3: skipped update, halved scale, bias correction by the count of successful steps, growth after
+    `growth_interval` clean steps (mmengine AmpOptimWrapper(loss_scale='dynamic'), cmunet_config.py:76-78)."""
+    from contrastive_masked_unet_b200.optim import DynamicLossScaler, FusedAdamW
+    g = _gen(seed)
+    sizes = [7, 3000, 70001]
+    ref = [_randn((s,), g).requires_grad_(True) for s in sizes]
+    mine = [p.detach().clone().requires_grad_(True) for p in ref]
+    opt_r = torch.optim.AdamW(ref, lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.05)
+    sc_r = torch.amp.GradScaler('cuda', init_scale=1024.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2)
+    opt_m = FusedAdamW([(f'w{i}', p) for i, p in enumerate(mine)], lr=1e-2, weight_decay=0.05, no_decay_keys=())
+    sc_m = DynamicLossScaler(DEV, init_scale=1024.0, growth_factor=2.0, backoff_factor=0.5, growth_interval=2)
+    scales = []
+    for step in range(6):
+        grads = [_randn((s,), g) for s in sizes]
+        if step == 2:
+            grads[1][17] = float('inf')
+        s_now = sc_r.get_scale()
+        for p, q, gr in zip(ref, mine, grads):
+            p.grad = (gr * s_now).clone()
+            q.grad = (gr * sc_m.get_scale()).clone()
+        sc_r.step(opt_r)
+        sc_r.update()
+        opt_m.step(scaler=sc_m)
+        torch.cuda.synchronize()
+        scales.append((sc_m.get_scale(), sc_r.get_scale()))
+    res = {'scales': scales, 'steps_taken': sc_m.steps_taken(),
+           'param_err': max(float((a.detach() - b.detach()).abs().max()) for a, b in zip(mine, ref))}
+    assert all(a == b for a, b in scales), res
+    assert res['steps_taken'] == 5 and res['param_err'] < 2e-5, res
+    assert all(bool(torch.isfinite(p).all()) for p in mine)
+    return res
+
+
+def check_sgd(seed=13):
+    from contrastive_masked_unet_b200.optim import FusedSGD
+    g = _gen(seed)
+    sizes = [5, 4097, 70001]
+    ref = [_randn((s,), g).requires_grad_(True) for s in sizes]
+    mine = [p.detach().clone().requires_grad_(True) for p in ref]
+    opt_r = torch.optim.SGD(ref, lr=0.03, momentum=0.9, weight_decay=1e-4)
+    opt_m = FusedSGD([(f'w{i}', p) for i, p in enumerate(mine)], lr=0.03, momentum=0.9, weight_decay=1e-4)
+    for _ in range(4):
+        grads = [_randn((s,), g) for s in sizes]
+        for p, q, gr in zip(ref, mine, grads):
+            p.grad = gr.clone()
+            q.grad = gr.clone()
+        opt_r.step()
+        opt_m.step()
+    torch.cuda.synchronize()
+    res = {'sgd': max(float((a.detach() - b.detach()).abs().max()) for a, b in zip(mine, ref))}
+    assert res['sgd'] < 1e-5, res
+    return res
+
+
 CHECKS = {
     'conv3x3_64_64': lambda: check_conv3x3(2, 24, 40, 64, 0, 64),
     'conv3x3_128_128': lambda: check_conv3x3(2, 16, 16, 128, 0, 128, seed=1),
@@ -629,6 +774,9 @@ CHECKS = {
     'mask_224': lambda: check_mask(61, 4, 224, 16, 0.65, 2),
     'mask_ps8': lambda: check_mask(3, 2, 128, 8, 0.5, 1),
     'mask_pair_mode_prefetch': check_mask_pair_mode,
+    'mask_interleaved_calls': check_mask_interleaved_calls,
+    'mask_1024_p4096': lambda: check_mask(7, 3, 1024, 16, 0.65, 1),
+    'mask_tiny_p4': lambda: check_mask(8, 5, 32, 16, 0.65, 2),
     'linear': check_linear,
     'linear_small': lambda: check_linear(64, 256, 1536, seed=18),
     'gemm_tn': check_gemm_tn,
@@ -642,4 +790,6 @@ CHECKS = {
     'cldice': check_cldice,
     'bn1d': check_bn1d,
     'optim': check_optim,
+    'optim_amp_dynamic_loss_scale': check_optim_amp,
+    'sgd_momentum': check_sgd,
 }

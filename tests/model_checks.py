@@ -7,10 +7,14 @@ be reached everywhere by ANY bf16 implementation: the contrastive branch normali
 the batch (SyncBN, nonlinear_neck.py:95) and sharpens with 1/tau = 14, which amplifies the ~2^-9 relative rounding of
 bf16 activations -- torch's own bf16 autocast of the oracle lands at the same cosines (see tools/grad_report.py and
 DESIGN.md "Numerics").  The test therefore requires, per parameter,
-    cos(cuda path, fp32 oracle) >= min(0.999, cos(torch bf16 autocast of the oracle, fp32 oracle) - 0.06)
+    cos(cuda path, fp32 oracle) >= min(0.999, cos(torch bf16 autocast of the oracle, fp32 oracle) - band)
 i.e. never worse than the reference run under its own mixed-precision mode, and 0.999 wherever that mode reaches it.
-(The 0.06 band: on the ill-conditioned parameters both cosines move by about +-0.01 from run to run -- fp32 atomics in
-the statistics reductions -- and the CUDA path typically sits 0.01 below autocast; a wrong kernel lands far below 0.9.)
+band = 0.02 at the benchmark configuration (B = 64 @ 512^2, where the floor is additionally the bf16-rounding
+emulation of the oracle: check_split_parity below; measured need: 0.008) and 0.04 for the small-batch cases (B <= 16:
+SyncBN statistics over few rows, measured need up to 0.022).  Why two correct bf16 implementations cannot agree better
+than that on this model -- rounding noise decorrelates within ~4 layers, and rounding ONLY the conv weights already
+costs 0.02-0.05 of cosine on the loss_ct gradients -- is measured by tools/noise_probe.py
+(profiles/r2_noise_probe_S512_B64.md).  A wrong kernel lands far below 0.9.
 Conv biases in front of a train-mode BN (analytically zero gradient) and pixel_decoder.conv_last channel 0 (quirk Q5)
 are compared absolutely."""
 import json
@@ -34,8 +38,12 @@ def cosine(a, b):
 
 
 def is_zero_grad_key(k):
-    """conv biases feeding train-mode BN: double_conv.{0,3}.bias."""
-    return k.endswith('double_conv.0.bias') or k.endswith('double_conv.3.bias')
+    """Biases whose gradient is analytically zero because a train-mode BatchNorm removes any per-channel constant:
+    conv biases double_conv.{0,3}.bias; the fc0 biases of the projector / predictor (BatchNorm1d follows,
+    nonlinear_neck.py:94-95); feature_decoder.conv_last.bias (a constant added to every pixel passes channel-mean and
+    fc0 as a per-feature constant, removed by bn0)."""
+    return k.endswith('double_conv.0.bias') or k.endswith('double_conv.3.bias') or \
+        k in ('projector.fc0.bias', 'head.predictor.fc0.bias', 'feature_decoder.conv_last.bias')
 
 
 def build_pair(S, seed):
@@ -72,7 +80,7 @@ def autocast_cosines(S, B, seed, data_seed, o_fp32_grads):
 
 
 def pretrain_parity(S=64, B=8, seed=60, data_seed=1, golden=None, grad_cos=0.999, loss_rtol=1e-2, verbose=False,
-                    autocast_ref=True, margin=0.06):
+                    autocast_ref=True, margin=0.04):
     m, o = build_pair(S, seed)
     img, img_t = O.synthetic_batch(B, S, data_seed)
     img, img_t = img.to(DEV), img_t.to(DEV)
@@ -373,3 +381,184 @@ def golden_pretrain(S, B):
 
 def golden_finetune():
     return json.load(open(os.path.join(GOLD, 'finetune.json')))['case']
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Split-loss gradient parity ("next round" 1): loss_rc-only, loss_ct-only and summed backward of ONE forward,
+# per parameter, at any (S, B) up to the benchmark configuration (B = 64 @ 512^2).  The three models (fp32 oracle, CUDA
+# drop-in, optionally torch's bf16 autocast of the oracle) are run one after the other and freed, so the fp32 oracle
+# (~135 GB of saved activations at B = 64 @ 512^2) and the bf16 drop-in (~57 GB) never coexist.
+# ------------------------------------------------------------------------------------------------------------------
+def _split_grads(model, img, img_t, seed, autocast=False):
+    """-> (losses, {name: (g_rc | None, g_ct | None)}) from one forward and two backward passes."""
+    import contextlib
+    torch.manual_seed(seed + 1000)                      # Q3: CPU RNG draw of the fresh reduce_channels conv
+    ctx = torch.autocast('cuda', dtype=torch.bfloat16) if autocast else contextlib.nullcontext()
+    with ctx:
+        out = model(img, mode='loss', img_t=img_t)
+    named = [(k, p) for k, p in model.named_parameters() if p.requires_grad]
+    ps = [p for _, p in named]
+    g_rc = torch.autograd.grad(out['loss_rc'], ps, retain_graph=True, allow_unused=True)
+    g_ct = torch.autograd.grad(out['loss_ct'], ps, allow_unused=True)
+    torch.cuda.synchronize()
+    losses = {'loss_ct': float(out['loss_ct']), 'loss_rc': float(out['loss_rc'])}
+    grads = {k: (None if a is None else a.detach().float(), None if b is None else b.detach().float())
+             for (k, _), a, b in zip(named, g_rc, g_ct)}
+    return losses, grads
+
+
+def _fresh(kind, S, seed):
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    if kind == 'cuda':
+        m = C.build(C.cmunet_config(S))
+    else:
+        m = O.OracleCMUNet(img_size=S, np_seed=seed)
+    m.init_weights()
+    return m.to(DEV).train()
+
+
+def _param_cos(k, g, go):
+    """cosine of one parameter's gradient with the oracle's, honouring the by-construction-zero entries."""
+    if g is None or go is None:
+        return None
+    if k == 'pixel_decoder.conv_last.weight':            # Q5: channel 0 has exactly zero gradient
+        return cosine(g[1], go[1])
+    if k == 'pixel_decoder.conv_last.bias':
+        return 1.0 - min(1.0, abs(float(g[1] - go[1])) / max(abs(float(go[1])), 1e-30))
+    return cosine(g, go)
+
+
+def split_grad_parity(S=512, B=64, seed=60, data_seed=1, with_autocast=True, with_emulation=True):
+    """Per-parameter cosine table vs the fp32 oracle for the three backward variants.  Returns
+    {'losses': {...}, 'table': {name: {'rc','ct','sum','rc_ac','ct_ac','sum_ac','norm_rc','norm_ct'}}}."""
+    img, img_t = O.synthetic_batch(B, S, data_seed)
+    img, img_t = img.to(DEV), img_t.to(DEV)
+    o = _fresh('oracle', S, seed)
+    lo, go = _split_grads(o, img, img_t, seed)
+    del o
+    torch.cuda.empty_cache()
+    m = _fresh('cuda', S, seed)
+    lm, gm = _split_grads(m, img, img_t, seed)
+    del m
+    torch.cuda.empty_cache()
+    le, ge = None, {}
+    if with_emulation:
+        # fp32 arithmetic + bf16 rounding exactly where the CUDA path stores / feeds bf16 (oracle/bf16_emulation.py)
+        from oracle import bf16_emulation as E
+        from oracle.mask_oracle import MT19937, patch_mask
+        e = _fresh('oracle', S, seed)
+        mask, _ = patch_mask(MT19937(seed), B, S, 16, 0.65)
+        torch.manual_seed(seed + 1000)
+        rc = torch.nn.Conv2d(1024, 256, kernel_size=1).to(DEV)                      # the Q3 draw of this step
+        out = E.forward_train(e, img, img_t, mask, rc.weight.detach(), rc.bias.detach(), **E.faithful(B))
+        named = [(k, p) for k, p in e.named_parameters() if p.requires_grad]
+        g_rc = torch.autograd.grad(out['loss_rc'], [p for _, p in named], retain_graph=True, allow_unused=True)
+        g_ct = torch.autograd.grad(out['loss_ct'], [p for _, p in named], allow_unused=True)
+        le = {'loss_ct': float(out['loss_ct']), 'loss_rc': float(out['loss_rc'])}
+        ge = {k: (a, b) for (k, _), a, b in zip(named, g_rc, g_ct)}
+        del e, out
+        torch.cuda.empty_cache()
+    la, ga = None, {}
+    if with_autocast:
+        a = _fresh('oracle', S, seed)
+        la, ga = _split_grads(a, img, img_t, seed, autocast=True)
+        del a
+        torch.cuda.empty_cache()
+
+    def total(pair):
+        r, c = pair
+        if r is None:
+            return c
+        return r if c is None else r + c
+
+    table = {}
+    for k, (orc, oct_) in go.items():
+        if is_zero_grad_key(k):
+            mr, mc = gm[k]
+            worst = max(float(x.abs().max()) for x in (mr, mc) if x is not None) if (mr is not None or mc is not None) else 0.0
+            table[k] = {'zero_by_construction': True, 'max_abs': worst}
+            continue
+        row = {'norm_rc': None if orc is None else float(orc.norm()), 'norm_ct': None if oct_ is None else float(oct_.norm())}
+        mr, mc = gm[k]
+        row['rc'] = _param_cos(k, mr, orc)
+        row['ct'] = _param_cos(k, mc, oct_)
+        row['sum'] = _param_cos(k, total(gm[k]), total(go[k]))
+        if k in ga:
+            ar, ac_ = ga[k]
+            row['rc_ac'] = _param_cos(k, ar, orc)
+            row['ct_ac'] = _param_cos(k, ac_, oct_)
+            row['sum_ac'] = _param_cos(k, total(ga[k]), total(go[k]))
+        if k in ge:
+            er, ec = ge[k]
+            row['rc_em'] = _param_cos(k, mr, er)
+            row['ct_em'] = _param_cos(k, mc, ec)
+            row['sum_em'] = _param_cos(k, total(gm[k]), total(ge[k]))
+            row['rc_emf'] = _param_cos(k, er, orc)                  # the emulation's own distance from fp32
+            row['ct_emf'] = _param_cos(k, ec, oct_)
+            row['sum_emf'] = _param_cos(k, total(ge[k]), total(go[k]))
+        if (mr is None) != (orc is None) or (mc is None) != (oct_ is None):
+            row['presence_mismatch'] = True
+        table[k] = row
+    return {'S': S, 'B': B, 'losses': {'cuda': lm, 'oracle': lo, 'autocast': la, 'bf16_emulation': le}, 'table': table}
+
+
+def summarize_split(rep):
+    """worst / count statistics per backward variant (rows with an oracle gradient norm under 1e-12 are noise)."""
+    out = {}
+    for var in ('rc', 'ct', 'sum'):
+        vals = [(r[var], k) for k, r in rep['table'].items() if not r.get('zero_by_construction') and r.get(var) is not None]
+        acs = [r[var + '_ac'] for k, r in rep['table'].items() if not r.get('zero_by_construction') and r.get(var + '_ac') is not None]
+        if not vals:
+            continue
+        out[var] = {'n': len(vals), 'worst': min(vals), 'n_ge_0.999': sum(1 for v, _ in vals if v >= 0.999),
+                    'mean': sum(v for v, _ in vals) / len(vals)}
+        ems = [(r[var + '_em'], k) for k, r in rep['table'].items() if not r.get('zero_by_construction') and r.get(var + '_em') is not None]
+        if ems:
+            out[var]['vs_emulation_worst'] = min(ems)
+            out[var]['vs_emulation_n_ge_0.999'] = sum(1 for v, _ in ems if v >= 0.999)
+        emf = [r[var + '_emf'] for k, r in rep['table'].items() if not r.get('zero_by_construction') and r.get(var + '_emf') is not None]
+        if emf:
+            out[var]['emulation_worst'] = min(emf)
+            out[var]['emulation_mean'] = sum(emf) / len(emf)
+            out[var]['emulation_n_ge_0.999'] = sum(1 for v in emf if v >= 0.999)
+        if acs:
+            out[var]['autocast_worst'] = min(acs)
+            out[var]['autocast_mean'] = sum(acs) / len(acs)
+            out[var]['autocast_n_ge_0.999'] = sum(1 for v in acs if v >= 0.999)
+    return out
+
+
+def check_split_parity(rep, band=0.02, loss_rtol=1e-2, zero_abs=1e-4):
+    """Pass/fail rules of the split-loss parity report:
+      * loss_ct, loss_rc within `loss_rtol` (north star: 1e-2) of the fp32 oracle, no widening;
+      * gradient presence identical (which loss reaches which parameter);
+      * by-construction-zero gradients are zero to `zero_abs`;
+      * per parameter and per backward variant (rc-only, ct-only, sum):
+            cos(cuda, fp32) >= min(0.999, floor - band),  floor = min(cos(torch bf16 autocast, fp32), cos(bf16 emulation, fp32))
+        i.e. 0.999 wherever bf16 operands can reach it at all, and elsewhere never further from the fp32 reference than
+        the two independent bf16 realisations of the same model (their own run-to-run spread is <= 0.01 at B = 64).
+        Gradients that are pure cancellation noise in every bf16 run (floor < 0.9: the ConvTranspose biases of the
+        feature decoder under loss_ct) only have to stay within 0.25 of that floor."""
+    fails = []
+    for name in ('loss_ct', 'loss_rc'):
+        a, b = rep['losses']['cuda'][name], rep['losses']['oracle'][name]
+        if abs(a - b) > loss_rtol * abs(b):
+            fails.append(f'{name}: {a} vs fp32 oracle {b}')
+    for k, r in rep['table'].items():
+        if r.get('zero_by_construction'):
+            if r['max_abs'] > zero_abs:
+                fails.append(f'{k}: expected a zero gradient, max abs {r["max_abs"]}')
+            continue
+        if r.get('presence_mismatch'):
+            fails.append(f'{k}: gradient presence differs from the oracle')
+            continue
+        for var in ('rc', 'ct', 'sum'):
+            c = r.get(var)
+            if c is None:
+                continue
+            refs = [r[x] for x in (var + '_ac', var + '_emf') if r.get(x) is not None]
+            need = 0.999 if not refs else min(0.999, min(refs) - (band if min(refs) >= 0.9 else 0.25))
+            if c < need:
+                fails.append(f'{k} [{var}]: cosine {c:.5f} < {need:.5f} (autocast {r.get(var + "_ac")}, emulation {r.get(var + "_emf")})')
+    return fails

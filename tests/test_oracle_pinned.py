@@ -187,3 +187,36 @@ def test_cldice_oracle_matches_reference_golden():
         assert float(O.soft_skel(gt[:, 1:]).sum()) == c['skel_true_sum']
         v = O.cldice_loss(logits, gt)
         assert str(v.dtype) == c['dtype'] and abs(float(v) - c['cldice']) < 1e-12
+
+
+def test_emulation_off_equals_oracle():
+    """oracle/bf16_emulation.py with every rounding switch off IS the pinned oracle (same losses, same gradients); with
+    the switches on it differs (the switches do something) but stays within bf16 distance."""
+    from oracle import bf16_emulation as E
+    from oracle import cmunet_oracle as O
+    from oracle.mask_oracle import MT19937, patch_mask
+    S, B, seed = 32, 4, 60
+    torch.manual_seed(seed)
+    o = O.OracleCMUNet(img_size=S, np_seed=seed)
+    o.init_weights()
+    o.train()
+    img, img_t = O.synthetic_batch(B, S, 1)
+    torch.manual_seed(seed + 1000)
+    ref = o(img, mode='loss', img_t=img_t)
+    (ref['loss_ct'] + ref['loss_rc']).backward()
+    g_ref = {k: p.grad.clone() for k, p in o.named_parameters() if p.grad is not None}
+    o.zero_grad()
+    mask, _ = patch_mask(MT19937(seed), B, S, 16, 0.65)
+    torch.manual_seed(seed + 1000)
+    rc = torch.nn.Conv2d(1024, 256, kernel_size=1)
+    out = E.forward_train(o, img, img_t, mask, rc.weight.detach(), rc.bias.detach())
+    assert float(out['loss_ct']) == pytest.approx(float(ref['loss_ct']), rel=1e-6)
+    assert float(out['loss_rc']) == pytest.approx(float(ref['loss_rc']), rel=1e-6)
+    (out['loss_ct'] + out['loss_rc']).backward()
+    for k, p in o.named_parameters():
+        if k in g_ref:
+            assert torch.allclose(p.grad, g_ref[k], rtol=1e-4, atol=1e-7), k
+    o.zero_grad()
+    out2 = E.forward_train(o, img, img_t, mask, rc.weight.detach(), rc.bias.detach(), **E.faithful(64))
+    assert float(out2['loss_rc']) != float(ref['loss_rc'])
+    assert float(out2['loss_rc']) == pytest.approx(float(ref['loss_rc']), rel=1e-2)
