@@ -3,14 +3,15 @@
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
   python bench.py --impl reference --gpus N --steps K --warmup W    (the reference's CPU path = pinned oracle port)
+  python bench.py --workload moco | finetune1024 ...       (BASELINE.json configs[3] / configs[4]; default: pretrain)
 
-A "step" is one full pretraining iteration of BASELINE.json configs[1] on every GPU: device patch-mask generation ->
-online + target encoder -> two decoders -> projector / InfoNCE + masked MSE -> backward (-> gradient all-reduce over
-NCCL when N>1, overlapped by DDP) -> fused AdamW -> EMA of the target networks.  Per-GPU batch 64 of synthetic
-1x512x512 images (weak scaling), random-init weights of the real architecture, bf16 activations / fp32 accumulate.
-`value` times K steps with inputs resident in HBM (CUDA events, max over ranks); `e2e` repeats the K steps through the
-public module API with pinned-host inputs copied H2D and the losses read back D2H inside the timed region.
-Prints ONE JSON line on rank 0.
+A "step" of the default workload is one full pretraining iteration of BASELINE.json configs[1] on every GPU: device
+patch-mask generation -> online + target encoder -> two decoders -> projector / InfoNCE + masked MSE -> backward
+(-> gradient all-reduce over NCCL when N>1, overlapped by DDP) -> fused AdamW -> EMA of the target networks.  Per-GPU
+batch 64 of synthetic 1x512x512 images (weak scaling), random-init weights of the real architecture, bf16 operands /
+fp32 accumulate.  `value` times K steps with inputs resident in HBM (CUDA events, max over ranks); `e2e` repeats the K
+steps through the public module API with pinned-host inputs copied H2D (copy stream, one step ahead) and every step's
+losses read back D2H inside the timed region.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -23,14 +24,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOPS_PER_IMAGE_512 = 2040.9e9          # algorithmic FLOPs of one pretraining step per image @512²
+FT_FLOPS_PER_IMAGE_1024 = 4616.0e9      # fine-tune UNet fwd+bwd per image @1024²
+ENC_FWD_FLOPS_512 = 135.59e9            # encoder forward per image @512²
 METRIC = 'CM-UNet pretrain images/sec @512^2'
+TRAFFIC_PROFILE = os.path.join(ROOT, 'profiles', 'step_dram_traffic.json')   # written by tools/ncu_aggregate.py
 
 
 def algorithmic_flops_per_image(S):
     return FLOPS_PER_IMAGE_512 * (S / 512.0) ** 2
-
-
-K1_DRAM_BYTES_PER_LAUNCH = 1.915e9   # measured, see roofline.traffic_note
 
 
 def measured_peaks():
@@ -40,6 +41,28 @@ def measured_peaks():
         return {'bf16_tflops': d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1400.0)), 'hbm_gbs': d.get('hbm_gbs', 6650.0),
                 'source': 'MEASURED_PEAKS.json (sustained bf16; kernels are timed inside a long step)'}
     return {'bf16_tflops': 1400.0, 'hbm_gbs': 6650.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+def committed_traffic():
+    """Per-launch DRAM traffic of the roofline kernels from the committed ncu aggregate (profiles/step_dram_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum per kernel family over one step of this command, with its date and
+    commit) -- NOT measured in this run (ncu cannot run inside the timed bench)."""
+    if not os.path.exists(TRAFFIC_PROFILE):
+        return None
+    d = json.load(open(TRAFFIC_PROFILE))
+    fam = d.get('families', {})
+
+    def per_launch(pred):
+        n = sum(v['launches'] for k, v in fam.items() if pred(k))
+        b = sum((v['dram_read_GB'] + v['dram_write_GB']) * 1e9 for k, v in fam.items() if pred(k))
+        return (b / n if n else None), n
+
+    k1, n1 = per_launch(lambda k: k.startswith('k1_pair_kernel'))
+    k2, n2 = per_launch(lambda k: k.startswith('k2_'))
+    return {'k1_bytes_per_launch': k1, 'k1_launches': n1, 'k2_bytes_per_launch': k2, 'k2_launches': n2,
+            'k2_algorithmic_bytes_per_step': d.get('k2_algorithmic_GB_per_step', None),
+            'k2_read_GB_per_step': sum(v['dram_read_GB'] for k, v in fam.items() if k.startswith('k2_')),
+            'step_total_GB': d.get('step_total_GB'), 'meta': d.get('meta')}
 
 
 class ClockSampler(threading.Thread):
@@ -78,54 +101,138 @@ class ClockSampler(threading.Thread):
                 'samples': len(s)}
 
 
-# ---------------------------------------------------------------------------------------------------- reference arm
-def cpu_oracle_step_time(B, S, steps, warmup, threads):
-    """fwd+bwd of the pinned oracle port (oracle/cmunet_oracle.py == the reference's CM_UNet, fp32) on the host cores."""
+# ---------------------------------------------------------------------------------------------------- CPU legs
+def cpu_oracle_step_time(workload, B, S, steps, warmup, threads):
+    """One training step of the pinned oracle port (fp32 torch CPU == the reference's modules) on the host cores."""
     import torch
     from oracle import cmunet_oracle as O
     torch.set_num_threads(threads)
     torch.manual_seed(60)
-    m = O.OracleCMUNet(img_size=S, np_seed=60)
-    m.init_weights()
-    m.train()
-    img, img_t = O.synthetic_batch(B, S, 1)
+    if workload == 'pretrain':
+        m = O.OracleCMUNet(img_size=S, np_seed=60)
+        m.init_weights()
+        m.train()
+        img, img_t = O.synthetic_batch(B, S, 1)
+
+        def one():
+            for p in m.parameters():
+                p.grad = None
+            out = m(img, mode='loss', img_t=img_t)
+            (out['loss_ct'] + out['loss_rc']).backward()
+            m.momentum_update()
+    elif workload == 'moco':
+        from oracle import moco_oracle as MO
+        m = MO.OracleMoco(emb_dim=1024, num_negatives=65536).train()
+        iq, ik = torch.rand(B, S, S), torch.rand(B, S, S)
+
+        def one():
+            for p in m.parameters():
+                p.grad = None
+            loss, _, _ = m.training_step(iq, ik)
+            loss.backward()
+    else:
+        m = O.OracleUNet().train()
+        x = torch.rand(B, S, S)
+        y1 = torch.rand(B, 1, S, S) > 0.9
+        y = torch.cat([~y1, y1], 1).double()
+
+        def one():
+            for p in m.parameters():
+                p.grad = None
+            pr = m(x)
+            (O.dice_loss(pr, y) + O.ce_prob_loss(pr, y)).backward()
     times = []
     for it in range(warmup + steps):
         t0 = time.time()
-        for p in m.parameters():
-            p.grad = None
-        out = m(img, mode='loss', img_t=img_t)
-        (out['loss_ct'] + out['loss_rc']).backward()
-        m.momentum_update()
-        dt = time.time() - t0
+        one()
         if it >= warmup:
-            times.append(dt)
+            times.append(time.time() - t0)
     return sum(times) / len(times)
 
 
+CPU_SAMPLE = {'pretrain': (2, 512), 'moco': (2, 512), 'finetune1024': (1, 1024)}   # bounded samples (B, S)
+
+
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path.  /root/reference does not exist on the GPU
+    box and the reference is pure Python on torch, so the arm is the pinned oracle PORT (kind = "port": oracle/
+    cmunet_oracle.py is held to golden vectors minted from the unmodified reference, tests/test_oracle_pinned.py)."""
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return
     import torch
     cores = os.cpu_count() or 1
-    B, S = 2, args.size
-    # bounded sample: the oracle at B=2, S=512 costs ~10-30 s/step on 8-32 host cores.  K and W are honoured up to
-    # 8 timed + 2 warm-up steps so that the whole run stays within a few minutes (the cap is reported in `config`).
+    B, S = CPU_SAMPLE[args.workload]
+    # bounded sample (~10-30 s of CPU work per step): K and W are honoured up to 6 timed + 2 warm-up steps so that the
+    # whole run stays within a few minutes; the line reports the counts that actually ran
     warm = max(1, min(args.warmup, 2))
-    steps = max(1, min(args.steps, 8))
-    t = cpu_oracle_step_time(B, S, steps, warm, cores)
+    steps = max(1, min(args.steps, 6))
+    t = cpu_oracle_step_time(args.workload, B, S, steps, warm, cores)
     val = B / t
-    line = {'metric': METRIC, 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+    line = {'metric': metric_name(args.workload), 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
+            'warmup': warm, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': f'configs[1] CM-UNet pretraining step (mask+fwd+bwd+EMA) at {S}x{S}, CPU, bounded sample',
-                       'per_step_batch': B, 'img_size': S, 'timed_steps_actually_run': steps, 'warmup_actually_run': warm},
+            'config': {'workload': workload_name(args.workload, B, S) + ' -- CPU, bounded sample', 'per_step_batch': B,
+                       'img_size': S, 'requested_steps': args.steps, 'requested_warmup': args.warmup,
+                       'note': 'steps / warmup above are the counts actually run (bounded CPU sample)'},
             'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                             'sample': f'{steps} timed fwd+bwd+EMA steps of the oracle port at B={B}, S={S} (fp32, torch CPU)'},
+                             'sample': f'{steps} timed + {warm} warm-up training steps of the oracle port at B={B}, S={S} '
+                                       '(fp32, torch CPU); the unmodified reference tree does not travel to the GPU box'},
             'e2e': {'value': val, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
+
+
+def metric_name(workload):
+    return {'pretrain': METRIC, 'moco': 'MoCo-v2 UNet pretrain images/sec @512^2 (65536-entry queue)',
+            'finetune1024': 'CM-UNet fine-tune images/sec @1024^2'}[workload]
+
+
+def workload_name(workload, B, S):
+    if workload == 'pretrain':
+        if (B, S) == (64, 512):
+            return ('configs[1]: CM-UNet pretraining step (patch mask + fwd + bwd + InfoNCE + masked MSE + AdamW + EMA), '
+                    'per-GPU batch 64 of synthetic 1x512x512')
+        return f'CM-UNet pretraining step at per-GPU batch {B}, {S}x{S}'
+    if workload == 'moco':
+        return (f'configs[3]: MoCo-v2 momentum-encoder UNet step (EMA + query/key encoders + queue InfoNCE over 65536 '
+                f'negatives + bwd + SGD + enqueue), per-GPU batch {B} of synthetic 1x{S}x{S}')
+    return (f'configs[4]: fine-tuning UNet step (fwd + Dice/CE + bwd + Adam), per-GPU batch {B} of synthetic '
+            f'1x{S}x{S} angiograms + binary masks')
+
+
+# ---------------------------------------------------------------------------------------------------- library baseline
+def torch_library_step(B, S, steps=2, warmup=1):
+    """Same-box LIBRARY comparator: the oracle port run through torch on this GPU the way a user of the
+    reference would run it on a B200 -- bf16 autocast, channels-last weights, cuDNN/cuBLAS kernels, torch.optim.AdamW
+    (fused), host-side numpy mask generation exactly as the reference does it.  Not the target, a same-box peer."""
+    import torch
+    from oracle import cmunet_oracle as O
+    torch.backends.cudnn.benchmark = True
+    torch.manual_seed(60)
+    m = O.OracleCMUNet(img_size=S, np_seed=60)
+    m.init_weights()
+    m = m.cuda().train().to(memory_format=torch.channels_last)
+    opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1.5e-4, betas=(0.9, 0.95), weight_decay=0.05,
+                            fused=True)
+    img, img_t = O.synthetic_batch(B, S, 1)
+    img, img_t = img.cuda(), img_t.cuda()
+    ts = []
+    for it in range(warmup + steps):
+        torch.cuda.synchronize()
+        t0 = time.time()
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            out = m(img, mode='loss', img_t=img_t)
+        (out['loss_ct'] + out['loss_rc']).backward()
+        opt.step()
+        m.momentum_update()
+        torch.cuda.synchronize()
+        if it >= warmup:
+            ts.append(time.time() - t0)
+    del m, opt
+    torch.cuda.empty_cache()
+    return sum(ts) / len(ts)
 
 
 # ---------------------------------------------------------------------------------------------------- our arm
@@ -145,38 +252,81 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     import contrastive_masked_unet_b200 as C
     from contrastive_masked_unet_b200 import ops
-    from contrastive_masked_unet_b200.optim import FusedAdamW
+    from contrastive_masked_unet_b200.optim import FusedAdamW, FusedSGD
     C.lib.cmu_device_check()
+    # the three forward branches run on three streams on purpose; autograd's stream-mismatch note is expected
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
 
-    B, S = args.batch, args.size
+    wl = args.workload
+    B = args.batch if args.batch else {'pretrain': 64, 'moco': 64, 'finetune1024': 16}[wl]
+    S = args.size if args.size else {'pretrain': 512, 'moco': 512, 'finetune1024': 1024}[wl]
     torch.manual_seed(60)
     np.random.seed(60 + rank)                      # cmunet_config.py:133 diff_rank_seed
-    model = C.build(C.cmunet_config(S))
-    model.init_weights()
-    model = model.to(dev).train()
-    core = model
-    if world > 1:
-        from torch.nn.parallel import DistributedDataParallel as DDP
-        model = DDP(core, device_ids=[local_rank], broadcast_buffers=False, gradient_as_bucket_view=True,
-                    bucket_cap_mb=64)
-    opt = FusedAdamW(core.named_parameters(), lr=1.5e-4)
-
-    # synthetic data: a few distinct batches (each 2 x 67 MB at B=64, S=512; activations per step are tens of GB, far
-    # beyond the 126 MB L2, so nothing is served from cache between steps)
     g = torch.Generator().manual_seed(1 + rank)
     n_pool = 2
-    host_img = [torch.randn(B, S, S, generator=g).pin_memory() for _ in range(n_pool)]
-    host_img_t = [(h + 0.1 * torch.randn(B, S, S, generator=g)).pin_memory() for h in host_img]
-    dev_img = [h.to(dev) for h in host_img]
-    dev_img_t = [h.to(dev) for h in host_img_t]
 
-    def step(img, img_t):
-        opt.zero_grad(set_to_none=True)
-        out = model(img, mode='loss', img_t=img_t)
-        (out['loss_ct'] + out['loss_rc']).backward()
-        opt.step()
-        core.momentum_update()
-        return out
+    def ddp(mod):
+        if world == 1:
+            return mod
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        return DDP(mod, device_ids=[local_rank], broadcast_buffers=False, gradient_as_bucket_view=True, bucket_cap_mb=64)
+
+    if wl == 'pretrain':
+        core = C.build(C.cmunet_config(S))
+        core.init_weights()
+        core = core.to(dev).train()
+        model = ddp(core)
+        opt = FusedAdamW(core.named_parameters(), lr=1.5e-4)
+        host_a = [torch.randn(B, S, S, generator=g).pin_memory() for _ in range(n_pool)]
+        host_b = [(h + 0.1 * torch.randn(B, S, S, generator=g)).pin_memory() for h in host_a]
+
+        def step(img, img_t):
+            opt.zero_grad(set_to_none=True)
+            out = model(img, mode='loss', img_t=img_t)
+            (out['loss_ct'] + out['loss_rc']).backward()
+            opt.step()
+            core.momentum_update()
+            return torch.stack([out['loss_ct'].detach(), out['loss_rc'].detach()])
+        flops_per_image = algorithmic_flops_per_image(S)
+    elif wl == 'moco':
+        core = C.Moco_v2(emb_dim=1024, num_negatives=65536).to(dev).train()
+        enc_q = ddp(core.encoder_q)                 # only the query encoder has gradients (moco2_module.py:140-146)
+        if world > 1:
+            core.encoder_q_ddp = enc_q
+        opt = FusedSGD(core.encoder_q.named_parameters(), lr=0.03, momentum=0.9, weight_decay=1e-4)
+        host_a = [torch.rand(B, S, S, generator=g).pin_memory() for _ in range(n_pool)]
+        host_b = [torch.rand(B, S, S, generator=g).pin_memory() for _ in range(n_pool)]
+
+        def step(img_q, img_k):
+            opt.zero_grad(set_to_none=True)
+            loss = core.training_step(img_q, img_k, encoder_q=enc_q)
+            loss.backward()
+            opt.step()
+            return loss.detach().reshape(1)
+        # query encoder fwd + dgrad + wgrad (first-layer dgrad not needed), key encoder fwd, queue logits fwd + dq
+        flops_per_image = (4 * ENC_FWD_FLOPS_512 - 0.302e9) * (S / 512.0) ** 2 + 2 * 2 * 65537 * 1024
+    else:
+        core = C.UNet().to(dev).train()
+        model = ddp(core)
+        opt = FusedAdamW(core.named_parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=0.0)   # Adam (FT/train.py:341-343)
+        loss_fn = C.DiceLoss(activation='softmax', threshold=0.5, ignore_channels=[0]) + C.CrossEntropyLoss()
+        host_a = [torch.rand(B, S, S, generator=g).pin_memory() for _ in range(n_pool)]
+        host_b = []
+        for _ in range(n_pool):
+            y1 = torch.rand(B, 1, S, S, generator=g) > 0.9
+            host_b.append(torch.cat([~y1, y1], 1).double().pin_memory())       # float64 one-hot targets (FT/dataset.py:48)
+
+        def step(x, y):
+            opt.zero_grad(set_to_none=True)
+            loss = loss_fn(model(x), y)
+            loss.backward()
+            opt.step()
+            return loss.detach().float().reshape(1)
+        flops_per_image = FT_FLOPS_PER_IMAGE_1024 * (S / 1024.0) ** 2
+
+    dev_a = [h.to(dev) for h in host_a]
+    dev_b = [h.to(dev) for h in host_b]
+    h2d_bytes = host_a[0].numel() * host_a[0].element_size() + host_b[0].numel() * host_b[0].element_size()
 
     def barrier():
         if world > 1:
@@ -184,7 +334,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for i in range(args.warmup):
-        step(dev_img[i % n_pool], dev_img_t[i % n_pool])
+        step(dev_a[i % n_pool], dev_b[i % n_pool])
     barrier()
 
     # ---- timed region 1: device-resident inputs
@@ -196,7 +346,7 @@ def run_ours(args):
     barrier()
     e0.record()
     for i in range(args.steps):
-        out = step(dev_img[i % n_pool], dev_img_t[i % n_pool])
+        out = step(dev_a[i % n_pool], dev_b[i % n_pool])
     e1.record()
     barrier()
     launches = C.lib.cmu_launch_count() - n0
@@ -206,41 +356,72 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms)
-    loss_ct, loss_rc = float(out['loss_ct']), float(out['loss_rc'])
+    last_losses = [float(v) for v in out]
 
-    # ---- timed region 2: end to end through the public API, pinned host inputs, losses read back
+    # ---- timed region 2: end to end through the public API.  Every step's inputs travel pinned host -> device inside the
+    # timed region (copy stream, issued one step ahead so that the 134 MB transfer overlaps the previous step), every
+    # step's losses travel device -> pinned host inside the timed region (read one step behind so that the host never
+    # stalls the launch queue; all of them are complete before the closing event).
     barrier()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+    host_out = [torch.empty(out.numel(), dtype=torch.float32).pin_memory() for _ in range(args.steps)]
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
+    copy_stream.wait_stream(main)                  # the first copy starts after the opening event
+
+    def fetch(i):
+        with torch.cuda.stream(copy_stream):
+            a = host_a[i % n_pool].to(dev, non_blocking=True)
+            b = host_b[i % n_pool].to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return a, b, ev
+
+    nxt = fetch(0)
+    d2h_events = []
     for i in range(args.steps):
-        img = host_img[i % n_pool].to(dev, non_blocking=True)
-        img_t = host_img_t[i % n_pool].to(dev, non_blocking=True)
-        o = step(img, img_t)
-        host_losses = torch.stack([o['loss_ct'].detach(), o['loss_rc'].detach()]).cpu()   # D2H read of the step's result
+        a, b, ev = nxt
+        if i + 1 < args.steps:
+            nxt = fetch(i + 1)
+        main.wait_event(ev)
+        a.record_stream(main)
+        b.record_stream(main)
+        o = step(a, b)
+        host_out[i].copy_(o, non_blocking=True)    # D2H of this step's result
+        dev_ev = torch.cuda.Event()
+        dev_ev.record()
+        d2h_events.append(dev_ev)
+        if i >= 1:
+            d2h_events[i - 1].synchronize()        # the previous step's losses are on the host now
+    d2h_events[-1].synchronize()
     e3.record()
     barrier()
     t2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     ms_e2e = float(t2)
+    assert all(bool(torch.isfinite(h).all()) for h in host_out)
 
-    # ---- roofline pass: the same K steps with CUDA events around every tensor-core launch.  The production schedule runs
-    # the target encoder and the two decoders on three streams; there an event pair also spans the time a kernel waits for
-    # SMs held by another stream's persistent kernel, so per-kernel durations are taken with the branches serialised on
-    # one stream (same kernels, same order, same clocks / power state).
+    # ---- roofline pass (pretrain / finetune): the same K steps with CUDA events around every tensor-core launch.  The
+    # production schedule runs the target encoder and the two decoders on three streams; there an event pair also spans
+    # the time a kernel waits for SMs held by another stream's persistent kernel, so per-kernel durations are taken with
+    # the branches serialised on one stream (same kernels, same order, same clocks / power state).
     timer = ops.KernelTimer()
-    core.multi_stream = False
-    step(dev_img[0], dev_img_t[0])
+    if wl == 'pretrain':
+        core.multi_stream = False
+    step(dev_a[0], dev_b[0])
     barrier()
     ops.PROFILER = timer
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e4.record()
     for i in range(args.steps):
-        step(dev_img[i % n_pool], dev_img_t[i % n_pool])
+        step(dev_a[i % n_pool], dev_b[i % n_pool])
     e5.record()
     barrier()
     ops.PROFILER = None
-    core.multi_stream = os.environ.get('CMU_SINGLE_STREAM') != '1'
+    if wl == 'pretrain':
+        core.multi_stream = os.environ.get('CMU_SINGLE_STREAM') != '1'
     ms_prof = e4.elapsed_time(e5)
 
     if rank == 0:
@@ -249,51 +430,85 @@ def run_ours(args):
         peaks = measured_peaks()
         summ = timer.summarize()
         tc_ms = sum(v[1] for v in summ.values())
-        tc_fl = sum(v[2] for v in summ.values())
-        # dominant kernel family: the tcgen05 implicit-GEMM convolution (K1: fprop + dgrad of every 3x3 conv)
-        k1 = [summ.get('conv3x3_fprop', (0, 0.0, 0.0)), summ.get('conv3x3_dgrad', (0, 0.0, 0.0))]
-        k1_ms, k1_fl, k1_n = sum(v[1] for v in k1), sum(v[2] for v in k1), sum(v[0] for v in k1)
-        achieved = (k1_fl / (k1_ms / 1e3)) / 1e12 if k1_ms > 0 else 0.0
-        roofline = {'bound': 'tensor', 'kernel': 'k1_kernel (tcgen05 implicit-GEMM conv3x3 fprop+dgrad)',
-                    'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                    'frac': achieved / peaks['bf16_tflops'],
-                    'traffic': K1_DRAM_BYTES_PER_LAUNCH if (B, S) == (64, 512) else None, 'peak_source': peaks['source'],
-                    'traffic_note': 'bytes per K1 launch, dram__bytes_read.sum + dram__bytes_write.sum averaged over the 60 '
-                                    'k1_pair launches of one step of this command (ncu, profiles/r1_k2_dram_traffic.md, '
-                                    'profiles/r1_step_dram_traffic.json); algorithmic bytes (every activation tile loaded '
-                                    'once, every output stored once) are the same 1.9 GB: no wasted re-reads',
-                    'launches': k1_n, 'avg_launch_ms': k1_ms / max(1, k1_n), 'share_of_step': k1_ms / ms_prof,
-                    'measured': f'CUDA events around every launch in a second pass of {args.steps} steps on ONE stream '
-                                f'({ms_prof / args.steps:.1f} ms/step; the 3-stream production schedule of the timed region '
-                                f'takes {ms / args.steps:.1f} ms/step)',
-                    'all_tensor_core_kernels': {k: {'launches': v[0], 'ms': round(v[1], 3),
-                                                    'tflops': round(v[2] / (v[1] / 1e3) / 1e12, 1) if v[1] > 0 else None}
-                                                for k, v in summ.items()},
-                    'tensor_core_share_of_step': tc_ms / ms_prof,
-                    'whole_step_algorithmic_tflops': algorithmic_flops_per_image(S) * value / 1e12,
-                    'whole_step_frac_of_peak': algorithmic_flops_per_image(S) * value / 1e12 / peaks['bf16_tflops']}
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            t = cpu_oracle_step_time(2, S, 1, 1 if S <= 256 else 0, cores)
-            cpu = {'value': 2 / t, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                   'sample': f'1 fwd+bwd+EMA step of the oracle port (fp32 torch CPU) at B=2, S={S}'}
-        line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
+        per_kernel = {k: {'launches': v[0], 'ms': round(v[1], 3),
+                          'tflops': round(v[2] / (v[1] / 1e3) / 1e12, 1) if v[1] > 0 else None} for k, v in summ.items()}
+        if wl == 'moco':
+            # dominant kernel of the queue head: logits GEMM lt[K][N] = Queue q^T, HBM-bound on the 134 MB bf16 queue
+            lg = summ.get('moco_logits', (0, 0.0, 0.0))
+            K, D = 65536, 1024
+            bytes_per_launch = K * D * 2 + B * D * 2 + K * B * 2        # queue rows + queries read, bf16 logits written
+            ach = bytes_per_launch * lg[0] / (lg[1] / 1e3) / 1e9 if lg[1] > 0 else 0.0
+            roofline = {'bound': 'hbm', 'kernel': 'moco queue logits (k1 1x1 engine: lt[K][N] = Queue q^T, K=65536, D=1024)',
+                        'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
+                        'traffic': None, 'algorithmic_bytes_per_launch': bytes_per_launch, 'launches': lg[0],
+                        'avg_launch_ms': lg[1] / max(1, lg[0]), 'peak_source': peaks['source']}
+        else:
+            # dominant kernel family: the tcgen05 implicit-GEMM convolution (K1: fprop + dgrad of every 3x3 conv)
+            k1 = [summ.get('conv3x3_fprop', (0, 0.0, 0.0)), summ.get('conv3x3_dgrad', (0, 0.0, 0.0))]
+            k1_ms, k1_fl, k1_n = sum(v[1] for v in k1), sum(v[2] for v in k1), sum(v[0] for v in k1)
+            achieved = (k1_fl / (k1_ms / 1e3)) / 1e12 if k1_ms > 0 else 0.0
+            tr = committed_traffic() if (wl, B, S) == ('pretrain', 64, 512) else None
+            roofline = {'bound': 'tensor', 'kernel': 'k1 (tcgen05 implicit-GEMM conv3x3 fprop+dgrad)',
+                        'achieved': achieved, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                        'frac': achieved / peaks['bf16_tflops'],
+                        'traffic': tr['k1_bytes_per_launch'] if tr else None, 'peak_source': peaks['source'],
+                        'traffic_source': ('profiles/step_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum '
+                                           'per launch, averaged over the k1_pair launches of one step of this command; '
+                                           f'NOT measured in this run) {tr["meta"]}') if tr else None,
+                        'k2_wgrad_traffic': ({'read_GB_per_step': tr['k2_read_GB_per_step'],
+                                              'algorithmic_GB_per_step': tr['k2_algorithmic_bytes_per_step'],
+                                              'ratio': (tr['k2_read_GB_per_step'] / tr['k2_algorithmic_bytes_per_step'])
+                                              if tr['k2_algorithmic_bytes_per_step'] else None}) if tr else None,
+                        'launches': k1_n, 'avg_launch_ms': k1_ms / max(1, k1_n), 'share_of_step': k1_ms / ms_prof,
+                        'measured': f'CUDA events around every launch in a second pass of {args.steps} steps on ONE stream '
+                                    f'({ms_prof / args.steps:.1f} ms/step; the production schedule of the timed region '
+                                    f'takes {ms / args.steps:.1f} ms/step)'}
+        roofline.update({'all_tensor_core_kernels': per_kernel, 'tensor_core_share_of_step': tc_ms / ms_prof,
+                         'whole_step_algorithmic_tflops': flops_per_image * value / world / 1e12,
+                         'whole_step_frac_of_peak': flops_per_image * value / world / 1e12 / peaks['bf16_tflops']})
+        line = {'metric': metric_name(wl), 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
                 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-                'config': {'workload': 'configs[1]: CM-UNet pretraining step (patch mask + fwd + bwd + InfoNCE + masked MSE '
-                                       '+ AdamW + EMA), per-GPU batch 64 of synthetic 1x512x512' if (B, S) == (64, 512) else
-                                       f'CM-UNet pretraining step at per-GPU batch {B}, {S}x{S}',
-                           'per_gpu_batch': B, 'global_batch': B * world, 'img_size': S, 'parallelism': f'dp{world}',
-                           'l2': 'inputs 2x67 MB/step and >50 GB of activations per step: far larger than the 126 MB L2',
-                           'loss_ct': loss_ct, 'loss_rc': loss_rc},
+                'config': {'workload': workload_name(wl, B, S), 'per_gpu_batch': B, 'global_batch': B * world, 'img_size': S,
+                           'parallelism': f'dp{world}',
+                           'l2': f'inputs {h2d_bytes / 1e6:.0f} MB/step and tens of GB of activations per step: far larger '
+                                 'than the 126 MB L2', 'losses': last_losses},
                 'clocks': clocks,
-                'e2e': {'value': imgs / (ms_e2e / 1e3), 'unit': 'images/s', 'h2d_bytes_per_step': 2 * B * S * S * 4,
-                        'd2h_bytes_per_step': 8, 'ms_per_step': ms_e2e / args.steps},
+                'e2e': {'value': imgs / (ms_e2e / 1e3), 'unit': 'images/s', 'h2d_bytes_per_step': h2d_bytes,
+                        'd2h_bytes_per_step': 4 * out.numel(), 'ms_per_step': ms_e2e / args.steps,
+                        'how': 'pinned host -> device on a copy stream one step ahead; losses device -> pinned host every '
+                               'step, awaited one step behind; all inside the timed region'},
                 'gpu_launches': int(launches),
                 'roofline': roofline}
-        if cpu is not None:
-            line['cpu_baseline'] = cpu
+        if world == 1 and not args.no_cpu_baseline:
+            # free this arm's device memory first: the library comparator needs ~90 GB at B = 64 @ 512^2
+            if wl == 'pretrain':
+                del step, out, o, a, b, nxt
+                del model, core, opt, dev_a, dev_b
+                import gc
+                gc.collect()
+                torch.cuda.empty_cache()
+                try:
+                    lib_B = B
+                    try:
+                        t_lib = torch_library_step(lib_B, S)
+                    except torch.OutOfMemoryError:
+                        torch.cuda.empty_cache()
+                        lib_B = B // 2
+                        t_lib = torch_library_step(lib_B, S)
+                    line['library_baseline'] = {
+                        'value': lib_B / t_lib, 'unit': 'images/s', 'ms_per_step': t_lib * 1e3, 'per_step_batch': lib_B,
+                        'what': 'the oracle port (== reference modules) through torch on the SAME GPU: bf16 autocast, '
+                                'channels-last weights, cuDNN/cuBLAS, fused torch AdamW, EMA, host numpy mask generation as '
+                                'in the reference; 1 warm-up + 2 timed steps, wall clock with synchronize'}
+                except Exception as e:   # the comparator must never take the bench line down
+                    line['library_baseline'] = {'unavailable': f'{type(e).__name__}: {str(e)[:120]}'}
+            cores = os.cpu_count() or 1
+            cb, cs = CPU_SAMPLE[wl]
+            t = cpu_oracle_step_time(wl, cb, cs, 2, 1, cores)
+            line['cpu_baseline'] = {'value': cb / t, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                    'sample': f'1 warm-up + 2 timed training steps of the oracle port (fp32 torch CPU) at '
+                                              f'B={cb}, S={cs}'}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -305,8 +520,9 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=64)
-    ap.add_argument('--size', type=int, default=512)
+    ap.add_argument('--workload', default='pretrain', choices=['pretrain', 'moco', 'finetune1024'])
+    ap.add_argument('--batch', type=int, default=0)
+    ap.add_argument('--size', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':

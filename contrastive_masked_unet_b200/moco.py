@@ -59,7 +59,7 @@ class MocoLossFn(torch.autograd.Function):
         lib.cmu_moco_prep(q.data_ptr(), k.data_ptr(), n, d, qh16.data_ptr(), qh.data_ptr(), qnorm.data_ptr(),
                           lpos.data_ptr(), st)
         wv = 64 if kneg % 64 == 0 else 8 if kneg % 8 == 0 else 1                     # any (H,W) factorisation works
-        lt = ops.conv1x1_fprop(queue_rows.view(1, kneg // wv, wv, d), qh16, None)   # (K,N) bf16 = Queue q_hat^T
+        lt = ops.conv1x1_fprop(queue_rows.view(1, kneg // wv, wv, d), qh16, None, name='moco_logits')   # (K,N) bf16 = Queue q_hat^T
         need = ctx.needs_input_grad[0]
         rows = torch.empty(n, device=dev)
         loss = torch.empty(1, device=dev)
@@ -199,10 +199,12 @@ class Moco_v2(nn.Module):
                            ops._stream())
 
     # ------------------------------------------------------------------ step
-    def forward(self, img_q, img_k, queue=None):
-        """-> (loss, k, q).  Unlike moco2_module.py:224-270 the (N, 1+K) logits tensor is not returned: it never exists."""
+    def forward(self, img_q, img_k, queue=None, encoder_q=None):
+        """-> (loss, k, q).  Unlike moco2_module.py:224-270 the (N, 1+K) logits tensor is not returned: it never exists.
+        encoder_q: optional wrapper of `self.encoder_q` to call instead (DistributedDataParallel around the only
+        sub-module that has gradients)."""
         ops._need_cuda(img_q, img_k)
-        q = self.encoder_q(img_q)
+        q = (encoder_q if encoder_q is not None else self.encoder_q)(img_q)
         with torch.no_grad():
             shuffle = self.shuffle_bn and _world() > 1            # moco2_module.py:246-255 (`_use_ddp_or_ddp2`)
             if shuffle:
@@ -213,11 +215,11 @@ class Moco_v2(nn.Module):
         loss = MocoLossFn.apply(q, k, self._queue_rows(), self.hparams['softmax_temperature'])
         return loss, k, q
 
-    def training_step(self, img_q, img_k):
+    def training_step(self, img_q, img_k, encoder_q=None):
         """moco2_module.py:287-309 without the Lightning plumbing: EMA of the key encoder, loss, dequeue/enqueue."""
         ops._need_cuda(img_q, img_k)
         self._momentum_update_key_encoder()
-        loss, k, _ = self.forward(img_q, img_k)
+        loss, k, _ = self.forward(img_q, img_k, encoder_q=encoder_q)
         self._dequeue_and_enqueue(k)
         return loss
 

@@ -283,11 +283,11 @@ def colsum_bf16(x2d_rows, c, x):
 
 
 # ------------------------------------------------------------------------------------------- 1x1
-def conv1x1_fprop(x, w_bf16, bias):
+def conv1x1_fprop(x, w_bf16, bias, name='conv1x1_fprop'):
     n, h, w, cin = _act(x).shape
     cout = w_bf16.shape[0]
     y = torch.empty(n, h, w, cout, dtype=BF16, device=x.device)
-    with _timed('conv1x1_fprop', 2.0 * n * h * w * cin * cout):
+    with _timed(name, 2.0 * n * h * w * cin * cout):
         lib.cmu_conv1x1_fprop(_ptr(x), cin, n, h, w, _ptr(w_bf16), cout, _ptr(bias), _ptr(y), _stream())
     return y
 

@@ -689,6 +689,7 @@ def check_optim_amp(seed=12):
         grads = [_randn((s,), g) for s in sizes]
         if step == 2:
             grads[1][17] = float('inf')
+        sc_r.scale(torch.zeros(1, device=DEV))            # GradScaler initialises its device scale lazily in scale()
         s_now = sc_r.get_scale()
         for p, q, gr in zip(ref, mine, grads):
             p.grad = (gr * s_now).clone()
