@@ -8,6 +8,7 @@ from .modules import (CM_UNet, CMUNetPretrainHead, DoubleConv, DownBlock, MaskSt
 from .finetune import CrossEntropyLoss, DiceLoss, IoU, Loss, Metric, MultipliedLoss, SumOfLosses, UNet, soft_cldice  # noqa: F401
 
 from .moco import Moco_v2, MocoUNetEncoder  # noqa: F401
+from .data import CMUNetGpuPipeline, SampleParams  # noqa: F401
 
 __version__ = '0.1.0'
 

@@ -12,7 +12,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'cmu_b200.h')
 
 _SCALARS = {
     'int': ctypes.c_int, 'long long': ctypes.c_longlong, 'float': ctypes.c_float, 'double': ctypes.c_double,
-    'unsigned int': ctypes.c_uint,
+    'unsigned int': ctypes.c_uint, 'unsigned long long': ctypes.c_ulonglong,
 }
 
 

@@ -18,6 +18,10 @@ FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std
          '--expt-relaxed-constexpr', '-Xptxas', '-v']
 
 
+# per-file extra flags: the data pipeline must round like Pillow / numpy (no contracted multiply-adds)
+EXTRA_FLAGS = {'data_aug.cu': ['-fmad=false']}
+
+
 def sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
 
@@ -42,7 +46,8 @@ def build(force=False, verbose=False):
 
     def compile_one(job):
         s, o = job
-        r = subprocess.run([NVCC] + FLAGS + ['-c', s, '-o', o], capture_output=True, text=True)
+        r = subprocess.run([NVCC] + FLAGS + EXTRA_FLAGS.get(os.path.basename(s), []) + ['-c', s, '-o', o],
+                           capture_output=True, text=True)
         return s, r
 
     failed = False

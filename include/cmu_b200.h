@@ -175,6 +175,21 @@ int cmu_adamw_chunks_amp(const long long* d_table, int n_chunks, float lr, float
 int cmu_sgd_chunks(const long long* d_table /* [n][4] = p, g, momentum buffer, count */, int n_chunks, float lr,
                    float momentum, float weight_decay, int first_step, void* stream);
 
+/* ---- f3  GPU data pipeline: Pretraining/CM-UNet/cmae/datasets/cmunet_dataset.py:74-88 -------------------------
+ * cmu_pil_resize_bicubic == `Image.fromarray(plane[y0:y0+h, x0:x0+w]).resize((out_w, out_h), Image.BICUBIC)` for n planes,
+ * bit-exact with Pillow for dtype 0 (uint8, mode "L") and 1 (float32, mode "F") -- replaces cmunet_dataset.py:77-78 and
+ * the crop + resize of RandomResizedCrop (cmae/datasets/pipelines/processing.py:570-590).  d_boxes: int32[n][4] =
+ * x0, y0, w, h or NULL (whole plane); tmp: n * src_h * out_w elements of the same dtype.
+ * cmu_aug_shift_flip_noise == RandomFlip decision + ShiftPixel (processing.py:97-121) + GaussNoise
+ * (auto_augment.py:1148-1154): img = crop at (0, 0), img_t = crop at (ph, pw) + max(crop)/10 * noise, cast back to the
+ * image dtype like `np.array(out, dtype=img.dtype)`; both returned as float32 model inputs.  d_params: int32[n][4] =
+ * flip, ph, pw, 0.  noise: explicit float64 N(0,1) field [n][crop][crop] (exact parity) or NULL -> Philox4x32-10(seed). */
+int cmu_pil_resize_bicubic(const void* src, int dtype, int n, int src_h, int src_w, const int* d_boxes, void* tmp,
+                           void* dst, int out_h, int out_w, void* stream);
+int cmu_aug_shift_flip_noise(const void* src, int dtype, int n, int src_h, int src_w, const int* d_params,
+                             const double* noise, unsigned long long seed, int crop, float* img, float* img_t,
+                             void* stream);
+
 /* ---- a15  fine-tuning losses: FT/metrics.py:135-220,503-504 ----------------------------------------------- */
 int cmu_seg_losses(const float* logits, const double* gt, double* acc /* double[4] */, double* out /* dice, iou, ce */,
                    float* dlogits /* or NULL */, const float* gscale, int n, int h, int w, double dice_eps, double beta,

@@ -12,3 +12,14 @@ def digit_version(version_str, length=4):
         parts.append(int(digits) if digits else 0)
     parts = (parts + [0] * length)[:length]
     return tuple(parts)
+
+
+def is_seq_of(seq, expected_type, seq_type=None):
+    import collections.abc as abc
+    if not isinstance(seq, seq_type or abc.Sequence):
+        return False
+    return all(isinstance(x, expected_type) for x in seq)
+
+
+def is_list_of(seq, expected_type):
+    return is_seq_of(seq, expected_type, seq_type=list)

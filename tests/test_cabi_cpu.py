@@ -168,3 +168,33 @@ def test_moco_constructor_matches_reference_rng_order_and_keys():
             m.training_step(torch.rand(64, 32, 32), torch.rand(64, 32, 32))
     with pytest.raises(NotImplementedError):
         C.Moco_v2(use_mlp=True, num_negatives=64)
+
+
+def test_data_pipeline_host_draws_match_the_oracle_order():
+    """CMUNetGpuPipeline.draw_params consumes numpy's global RNG and python's `random` exactly like the restated
+    reference order (oracle/data_oracle.draw_sample_params, pinned to the reference by tests/test_oracle_data.py)."""
+    import random as pyrandom
+    import numpy as np
+    from oracle import data_oracle as D
+    pipe = C.CMUNetGpuPipeline()
+    np.random.seed(21)
+    pyrandom.seed(21)
+    prm = pipe.draw_params(6, host_noise=True)
+    np.random.seed(21)
+    pyrandom.seed(21)
+    for i in range(6):
+        o = D.draw_sample_params()
+        assert tuple(prm.crop[i]) == tuple(o['crop']) and prm.flip[i] == o['flip'] and tuple(prm.shift[i]) == tuple(o['shift'])
+        assert np.array_equal(prm.noise[i], o['noise'])
+    # both generators are left at the same position as after six reference-order draws
+    nxt, nxt_py = np.random.rand(), pyrandom.random()
+    np.random.seed(21)
+    pyrandom.seed(21)
+    for _ in range(6):
+        D.draw_sample_params()
+    assert np.random.rand() == nxt and pyrandom.random() == nxt_py
+    with pytest.raises(ValueError):
+        C.CMUNetGpuPipeline(base=256, out=240, pixel=31)
+    if not torch.cuda.is_available():
+        with pytest.raises(C.CmuError):
+            pipe(torch.zeros(1, 64, 64, dtype=torch.uint8), pipe.draw_params(1))
