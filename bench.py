@@ -328,14 +328,21 @@ def run_ours(args):
     dev_b = [h.to(dev) for h in host_b]
     h2d_bytes = host_a[0].numel() * host_a[0].element_size() + host_b[0].numel() * host_b[0].element_size()
 
-    def barrier():
+    verbose = os.environ.get('CMU_BENCH_VERBOSE') == '1'
+
+    def barrier(tag=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        if verbose and tag:
+            print(f'[bench rank {rank}] {tag}', file=sys.stderr, flush=True)
 
     for i in range(args.warmup):
         step(dev_a[i % n_pool], dev_b[i % n_pool])
-    barrier()
+        if verbose:
+            torch.cuda.synchronize()
+            print(f'[bench rank {rank}] warm-up step {i} done', file=sys.stderr, flush=True)
+    barrier('warm-up done')
 
     # ---- timed region 1: device-resident inputs
     sampler = ClockSampler(local_rank)
@@ -348,7 +355,7 @@ def run_ours(args):
     for i in range(args.steps):
         out = step(dev_a[i % n_pool], dev_b[i % n_pool])
     e1.record()
-    barrier()
+    barrier('timed region 1 done')
     launches = C.lib.cmu_launch_count() - n0
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
@@ -370,24 +377,33 @@ def run_ours(args):
     e2.record()
     copy_stream.wait_stream(main)                  # the first copy starts after the opening event
 
+    # two preallocated device staging slots (no allocator traffic inside the timed region); a slot is refilled only after
+    # the step that consumed it has finished (event), the copy of step i+1 overlaps the compute of step i
+    slots = [(torch.empty_like(dev_a[0]), torch.empty_like(dev_b[0])) for _ in range(2)]
+    consumed = [None, None]
+
     def fetch(i):
+        sa, sb = slots[i % 2]
         with torch.cuda.stream(copy_stream):
-            a = host_a[i % n_pool].to(dev, non_blocking=True)
-            b = host_b[i % n_pool].to(dev, non_blocking=True)
+            if consumed[i % 2] is not None:
+                copy_stream.wait_event(consumed[i % 2])
+            sa.copy_(host_a[i % n_pool], non_blocking=True)
+            sb.copy_(host_b[i % n_pool], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return a, b, ev
+        return sa, sb, ev
 
     nxt = fetch(0)
     d2h_events = []
     for i in range(args.steps):
         a, b, ev = nxt
+        main.wait_event(ev)
+        o = step(a, b)
+        done = torch.cuda.Event()
+        done.record(main)
+        consumed[i % 2] = done
         if i + 1 < args.steps:
             nxt = fetch(i + 1)
-        main.wait_event(ev)
-        a.record_stream(main)
-        b.record_stream(main)
-        o = step(a, b)
         host_out[i].copy_(o, non_blocking=True)    # D2H of this step's result
         dev_ev = torch.cuda.Event()
         dev_ev.record()
@@ -396,7 +412,7 @@ def run_ours(args):
             d2h_events[i - 1].synchronize()        # the previous step's losses are on the host now
     d2h_events[-1].synchronize()
     e3.record()
-    barrier()
+    barrier('e2e region done')
     t2 = torch.tensor([e2.elapsed_time(e3)], device=dev)
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
@@ -483,7 +499,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             # free this arm's device memory first: the library comparator needs ~90 GB at B = 64 @ 512^2
             if wl == 'pretrain':
-                del step, out, o, a, b, nxt
+                del step, out, o, a, b, nxt, slots
                 del model, core, opt, dev_a, dev_b
                 import gc
                 gc.collect()

@@ -33,7 +33,12 @@ struct K1Params {
   const float* bias;
   int bias_mod;
   float* stats;     // [gridDim.x][2][BN] partial (sum, sum of squares) or nullptr
+  float exp_scale;  // != 0: epilogue stores exp((acc - 1) * exp_scale) (MoCo queue logits -> unnormalised softmax terms)
 };
+
+// Shared memory the K1 kernels plan with.  Knob 14 = KB left free per SM so that blocks of the HBM-bound BatchNorm /
+// element-wise kernels of ANOTHER stream can be co-resident with a persistent tensor-core CTA (A/B).
+static inline int smem_budget() { return kSmemLimit - 1024 * debug_knob(14); }
 
 // staging / epilogue-group plan: two groups with two 16 KB buffers each when the pipeline keeps >= 4 stages, then two
 // groups with one buffer, else the single-group plans.  (Measured: the second group only helps ConvTranspose fprop,

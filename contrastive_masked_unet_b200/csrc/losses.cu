@@ -615,6 +615,25 @@ __global__ void __launch_bounds__(256) moco_softmax_kernel(const __nv_bfloat16* 
   }
 }
 // q_hat = q/|q| (bf16 copy for the GEMM), l_pos[n] = <q_hat, k_n>
+// Finishes the fused logits / softmax-numerator kernel: Z_n = sum_k E[k][n] + exp((lpos_n - 1)/T) from the per-CTA partial
+// column sums (layout of the convolution statistics: partial[grid][2][bn], channel c in rows r = c / bn (mod n_tiles)),
+// loss_n = log Z_n - (lpos_n - 1)/T, ppos_n = exp((lpos_n - 1)/T) / Z_n, row_scale_n = 1 / (Z_n * N * T).
+__global__ void moco_finish_kernel(const float* __restrict__ partial, int grid, int bn, int N, const float* __restrict__ lpos,
+                                   float inv_t, float* __restrict__ loss_rows, float* __restrict__ ppos,
+                                   float* __restrict__ row_scale) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int n_tiles = N / bn, nt = n / bn, c = n - nt * bn;
+  double z = 0.0;
+  for (int r = nt; r < grid; r += n_tiles) z += (double)partial[((size_t)r * 2) * bn + c];
+  const float lp = (lpos[n] - 1.f) * inv_t;
+  const float ep = __expf(lp);
+  const float zz = (float)z + ep;
+  loss_rows[n] = logf(zz) - lp;
+  ppos[n] = ep / zz;
+  row_scale[n] = inv_t / (zz * (float)N);
+}
+
 __global__ void __launch_bounds__(256) moco_prep_kernel(const float* __restrict__ q, const float* __restrict__ k, int D,
                                                         __nv_bfloat16* __restrict__ qh16, float* __restrict__ qh,
                                                         float* __restrict__ qnorm, float* __restrict__ lpos) {
@@ -649,13 +668,14 @@ __global__ void __launch_bounds__(256) moco_prep_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) moco_dq_kernel(const float* __restrict__ dq_neg, const float* __restrict__ k,
                                                       const float* __restrict__ qh, const float* __restrict__ qnorm,
                                                       const float* __restrict__ ppos, int D, float coef,
-                                                      float* __restrict__ dq) {
+                                                      float* __restrict__ dq, const float* __restrict__ row_scale) {
   __shared__ float sred[8];
   const int n = blockIdx.x, tid = threadIdx.x;
   const float cp = (ppos[n] - 1.f) * coef;
+  const float rs = row_scale != nullptr ? row_scale[n] : 1.f;   // dq_neg holds E^T Queue: normalise by 1 / (Z N T)
   float pg = 0.f;
   for (int d = tid; d < D; d += 256) {
-    const float g = dq_neg[(size_t)n * D + d] + cp * k[(size_t)n * D + d];
+    const float g = rs * dq_neg[(size_t)n * D + d] + cp * k[(size_t)n * D + d];
     pg += qh[(size_t)n * D + d] * g;
   }
   pg = warp_sum(pg);
@@ -665,7 +685,7 @@ __global__ void __launch_bounds__(256) moco_dq_kernel(const float* __restrict__ 
   for (int i = 0; i < 8; ++i) tot += sred[i];
   const float inv = 1.f / qnorm[n];
   for (int d = tid; d < D; d += 256) {
-    const float g = dq_neg[(size_t)n * D + d] + cp * k[(size_t)n * D + d];
+    const float g = rs * dq_neg[(size_t)n * D + d] + cp * k[(size_t)n * D + d];
     dq[(size_t)n * D + d] = (g - qh[(size_t)n * D + d] * tot) * inv;
   }
 }
@@ -716,7 +736,28 @@ int cmu_moco_softmax(const void* lt, const float* lpos, int k, int n, float temp
 }
 int cmu_moco_dq(const float* dq_neg, const float* k, const float* qh, const float* qnorm, const float* ppos, int n, int d,
                 float temperature, float* dq, void* stream) {
-  moco_dq_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(dq_neg, k, qh, qnorm, ppos, d, 1.f / ((float)n * temperature), dq);
+  moco_dq_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(dq_neg, k, qh, qnorm, ppos, d, 1.f / ((float)n * temperature), dq,
+                                                      nullptr);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_moco_finish(const float* sums_partial, int sums_grid, int sums_bn, int n, const float* lpos, float temperature,
+                    float* loss_rows, float* loss, float* ppos, float* row_scale, void* stream) {
+  CMU_REQUIRE(sums_bn > 0 && n % sums_bn == 0 && sums_grid >= n / sums_bn, "moco_finish: bad partial layout");
+  cudaStream_t st = (cudaStream_t)stream;
+  moco_finish_kernel<<<ceil_div(n, 128), 128, 0, st>>>(sums_partial, sums_grid, sums_bn, n, lpos, 1.f / temperature,
+                                                       loss_rows, ppos, row_scale);
+  CMU_LAUNCH_CHECK();
+  mean_scale_kernel<<<1, 32, 0, st>>>(loss_rows, n, 1.f, loss);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_moco_dq_scaled(const float* dq_neg_unnorm, const float* row_scale, const float* k, const float* qh,
+                       const float* qnorm, const float* ppos, int n, int d, float temperature, float* dq, void* stream) {
+  moco_dq_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(dq_neg_unnorm, k, qh, qnorm, ppos, d,
+                                                      1.f / ((float)n * temperature), dq, row_scale);
   CMU_LAUNCH_CHECK();
   return 0;
 }

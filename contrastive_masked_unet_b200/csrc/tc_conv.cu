@@ -278,6 +278,10 @@ __global__ void __launch_bounds__(kK1Threads, 1) k1_kernel(const __grid_constant
               v[4 * i + 3] += b4.w;
             }
           }
+          if (p.exp_scale != 0.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __expf((v[i] - 1.f) * p.exp_scale);
+          }
           // bf16 pack + swizzled staging store (16-byte chunk index XOR (row & 7): TMA SWIZZLE_128B pattern)
           uint8_t* rowp = stg + lane * 128;
 #pragma unroll
@@ -404,8 +408,9 @@ int simt_k1(int mode, const void* a0, int c0, const void* a1, int c1, int N, int
 
 static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int N, int H, int W, const void* wpk,
                   int n_total, void* out0, int oc0, void* out1, int oc1, const float* bias, int bias_mod,
-                  float* stats_partial, int* stats_grid, int* stats_bn, cudaStream_t stream) {
+                  float* stats_partial, int* stats_grid, int* stats_bn, cudaStream_t stream, float exp_scale = 0.f) {
   if (debug_knob(0) == 1) {  // CUDA-core cross-check path (tests / debugging only)
+    CMU_REQUIRE(exp_scale == 0.f, "k1: the CUDA-core cross-check path has no exp epilogue");
     if (stats_bn) *stats_bn = n_total;
     return simt_k1(mode, a0, c0, a1, c1, N, H, W, wpk, n_total, out0, oc0, out1, oc1, bias, bias_mod, stats_partial,
                    stats_grid, stream);
@@ -433,6 +438,7 @@ static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int 
   p.bias = bias;
   p.bias_mod = bias_mod > 0 ? bias_mod : n_total;
   p.stats = stats_partial;
+  p.exp_scale = exp_scale;
 
   const int box_h = (mode == MODE_CONV3) ? p.TH + 2 : p.TH;
   if (mode == MODE_CONVT_DGRAD) {
@@ -488,13 +494,13 @@ static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int 
   p.w_resident = 0;
   p.w_bytes = 0;
   if (debug_knob(4) != 1 && mode != MODE_CONVT_DGRAD && p.m_tiles >= 4 * num_sms() &&
-      (kSmemLimit - fixed - kStagingBytes - w_all) / p.b_off >= 3) {
+      (smem_budget() - fixed - kStagingBytes - w_all) / p.b_off >= 3) {
     p.w_resident = 1;
     p.w_bytes = w_all;
     p.stage_bytes = p.b_off;
   }
-  plan_epilogue(kSmemLimit - fixed - p.w_bytes, p.stage_bytes, debug_knob(9) == 1, &p.epi_groups, &p.stg_bufs);
-  p.n_stages = (kSmemLimit - fixed - p.w_bytes - p.epi_groups * p.stg_bufs * kStagingBytes) / p.stage_bytes;
+  plan_epilogue(smem_budget() - fixed - p.w_bytes, p.stage_bytes, debug_knob(9) == 1, &p.epi_groups, &p.stg_bufs);
+  p.n_stages = (smem_budget() - fixed - p.w_bytes - p.epi_groups * p.stg_bufs * kStagingBytes) / p.stage_bytes;
   if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
   CMU_REQUIRE(p.n_stages >= 2, "k1: shared-memory plan failed (stage %d bytes)", p.stage_bytes);
   const int smem_bytes = p.w_bytes + p.n_stages * p.stage_bytes + p.epi_groups * p.stg_bufs * kStagingBytes + fixed;
@@ -534,6 +540,16 @@ int cmu_conv1x1_fprop(const void* x, int cin, int n, int h, int w, const void* w
                       void* y, void* stream) {
   return run_k1(MODE_PLAIN, x, cin, nullptr, 0, n, h, w, w_packed, cout, y, cout, nullptr, 0, bias, cout, nullptr,
                 nullptr, nullptr, (cudaStream_t)stream);
+}
+
+// MoCo queue logits fused with the softmax numerator (moco2_module.py:258-266): y[p][c] = exp((x[p].w[c] - 1) / T) in
+// bf16 -- the logits themselves never reach HBM -- plus per-CTA partial column sums of the stored values (the softmax
+// denominators), in the layout of the convolution statistics: partial[grid][2][bn].
+int cmu_conv1x1_fprop_exp(const void* x, int cin, int n, int h, int w, const void* w_packed, int cout, float inv_temperature,
+                          void* y, float* sums_partial, int* sums_grid, int* sums_bn, void* stream) {
+  CMU_REQUIRE(inv_temperature > 0.f, "conv1x1_fprop_exp: 1/T must be positive");
+  return run_k1(MODE_PLAIN, x, cin, nullptr, 0, n, h, w, w_packed, cout, y, cout, nullptr, 0, nullptr, 0, sums_partial,
+                sums_grid, sums_bn, (cudaStream_t)stream, inv_temperature);
 }
 
 int cmu_convT2x2_fprop(const void* x, int cin, int n, int h, int w, const void* w_packed, int cout, const float* bias,

@@ -17,7 +17,10 @@
 //     BOTH CTAs;
 //   * the epilogue warps of both CTAs hand an accumulator back by arriving (remotely for the peer) on the leader's
 //     tmem-empty barrier (count 8).
-// Tiles are assigned statically per cluster (both CTAs must walk the same tile sequence).
+// Tiles are assigned statically per cluster (both CTAs must walk the same tile sequence).  A cluster-level dynamic
+// scheduler (leader pulls super-tiles from a global counter and publishes them to both CTAs through a DSMEM ring) was
+// built and measured in round 2: no gain at N = 1 (-0.5 %: the ring costs a GPU-scope release per tile) and sporadic
+// launch failures under load, so the static walk stays.
 // Also covered: ConvTranspose2d fprop (5-D scatter store) and dgrad (5-D .cta_group::2 gather); N = 64 tiles keep their
 // half of the weights resident in shared memory and stream activations only.
 #include "k1_common.cuh"
@@ -242,6 +245,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + cb + i);
           }
+          if (p.exp_scale != 0.f) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __expf((v[i] - 1.f) * p.exp_scale);
+          }
           uint8_t* rowp = stg + lane * 128;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
@@ -332,13 +339,13 @@ int run_k1_pair(K1Params& p, const void* wpk, int ktot, cudaStream_t stream, int
   // chunks per tile, so the TMA latency is hidden by the number of stages in flight, not by the length of a tile)
   const int w_all = p.kc * ((p.mode == MODE_CONV3) ? 3 : 1) * p.b_bytes;
   if (debug_knob(4) != 1 && BN == 64 && w_all <= 80 * 1024 &&
-      (kSmemLimit - fixed - 2 * kStagingBytes - w_all) / p.b_off >= 5) {
+      (smem_budget() - fixed - 2 * kStagingBytes - w_all) / p.b_off >= 5) {
     p.w_resident = 1;
     p.w_bytes = w_all;
     p.stage_bytes = p.b_off;
   }
-  plan_epilogue(kSmemLimit - fixed - p.w_bytes, p.stage_bytes, debug_knob(9) == 1, &p.epi_groups, &p.stg_bufs);
-  p.n_stages = (kSmemLimit - fixed - p.w_bytes - p.epi_groups * p.stg_bufs * kStagingBytes) / p.stage_bytes;
+  plan_epilogue(smem_budget() - fixed - p.w_bytes, p.stage_bytes, debug_knob(9) == 1, &p.epi_groups, &p.stg_bufs);
+  p.n_stages = (smem_budget() - fixed - p.w_bytes - p.epi_groups * p.stg_bufs * kStagingBytes) / p.stage_bytes;
   if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
   CMU_REQUIRE(p.n_stages >= 2, "k1 pair: shared-memory plan failed");
   const int smem_bytes = p.w_bytes + p.n_stages * p.stage_bytes + p.epi_groups * p.stg_bufs * kStagingBytes + fixed;

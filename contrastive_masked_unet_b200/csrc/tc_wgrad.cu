@@ -391,6 +391,7 @@ static int run_k2(int mode, const void* q0, int qc0, const void* q1, int qc1, co
   const int grid = pl.MT * pl.NT * pl.G * pl.splits;
   const int tiles_per_cta = ceil_div(pl.pix_tiles, pl.splits);
   p.n_stages = (debug_knob(12) != 1 && tiles_per_cta < kK2Stages) ? tiles_per_cta : kK2Stages;
+  if (debug_knob(15) == 2 && p.n_stages > 2) p.n_stages = 2;   // A/B: leave 72 KB of the SM to co-resident kernels
   const int smem_bytes = p.n_stages * kK2Stage + 1024 + 512;
   p.paced = (pl.G > 1 && debug_knob(10) == 1) ? 1 : 0;   // A/B: see profiles/r1_k2_dram_traffic.md
   if (p.paced) {

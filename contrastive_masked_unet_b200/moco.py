@@ -3,9 +3,10 @@ drop-in for the math of Pretraining/MoCo/pl_bolts/models/self_supervised/moco/mo
 Lightning shell (constructor keywords, buffers `queue` (D,K) / `queue_ptr` / `val_queue*`, `encoder_q` / `encoder_k`
 state_dict keys are kept).
 
-The N x (1+K) logits are never materialised in fp32: the negatives come out of the tcgen05 1x1 kernel as bf16
-`lt[K][N]` (queue rows are the GEMM-M "pixels", the normalised queries the weight matrix), one kernel does the online
-softmax-CE per query and emits the probabilities, and dq = P^T Queue runs on the tcgen05 row-reduction GEMM."""
+The N x (1+K) logits never reach HBM: the tcgen05 1x1 kernel (queue rows are the GEMM-M "pixels", the normalised
+queries the weight matrix) applies exp((logit - 1) / T) in its epilogue and stores the unnormalised softmax terms
+E[K][N] in bf16 together with per-CTA partial column sums (the denominators); a tiny kernel finishes loss, p(positive)
+and the per-query scale, and dq = (E^T Queue) * scale runs on the tcgen05 row-reduction GEMM."""
 import torch
 import torch.nn as nn
 
@@ -59,19 +60,22 @@ class MocoLossFn(torch.autograd.Function):
         lib.cmu_moco_prep(q.data_ptr(), k.data_ptr(), n, d, qh16.data_ptr(), qh.data_ptr(), qnorm.data_ptr(),
                           lpos.data_ptr(), st)
         wv = 64 if kneg % 64 == 0 else 8 if kneg % 8 == 0 else 1                     # any (H,W) factorisation works
-        lt = ops.conv1x1_fprop(queue_rows.view(1, kneg // wv, wv, d), qh16, None, name='moco_logits')   # (K,N) bf16 = Queue q_hat^T
+        # E[k][n] = exp((Queue_k . q_hat_n - 1) / T) straight from the tcgen05 epilogue (bf16) + partial column sums:
+        # the logits never reach HBM; E is the operand of the backward GEMM
+        e, part, grid, bn = ops.conv1x1_fprop_exp(queue_rows.view(1, kneg // wv, wv, d), qh16, 1.0 / float(temperature),
+                                                  name='moco_logits')
         need = ctx.needs_input_grad[0]
         rows = torch.empty(n, device=dev)
         loss = torch.empty(1, device=dev)
         ppos = torch.empty(n, device=dev)
-        pmat = torch.empty(kneg, n, dtype=BF16, device=dev) if need else None
-        lib.cmu_moco_softmax(lt.data_ptr(), lpos.data_ptr(), kneg, n, float(temperature), rows.data_ptr(),
-                             loss.data_ptr(), ppos.data_ptr(), ops._ptr(pmat), st)
+        rscale = torch.empty(n, device=dev)
+        lib.cmu_moco_finish(part.data_ptr(), grid, bn, n, lpos.data_ptr(), float(temperature), rows.data_ptr(),
+                            loss.data_ptr(), ppos.data_ptr(), rscale.data_ptr(), st)
         if need:
-            dq_neg = ops.gemm_tn(pmat, queue_rows)                                 # (N,D) = P^T Queue / (N T)
+            dq_neg = ops.gemm_tn(e.view(kneg, n), queue_rows)                      # (N,D) = E^T Queue (unnormalised)
             dq = torch.empty_like(q)
-            lib.cmu_moco_dq(dq_neg.data_ptr(), k.data_ptr(), qh.data_ptr(), qnorm.data_ptr(), ppos.data_ptr(), n, d,
-                            float(temperature), dq.data_ptr(), st)
+            lib.cmu_moco_dq_scaled(dq_neg.data_ptr(), rscale.data_ptr(), k.data_ptr(), qh.data_ptr(), qnorm.data_ptr(),
+                                   ppos.data_ptr(), n, d, float(temperature), dq.data_ptr(), st)
             ctx.save_for_backward(dq)
         return loss.reshape(())
 

@@ -292,6 +292,20 @@ def conv1x1_fprop(x, w_bf16, bias, name='conv1x1_fprop'):
     return y
 
 
+def conv1x1_fprop_exp(x, w_bf16, inv_temperature, name='conv1x1_fprop_exp'):
+    """y[p][c] = exp((x[p] . w[c] - 1) * inv_temperature) (bf16) and per-CTA partial column sums of y.
+    -> (y, partial, grid, bn_tile)"""
+    n, h, w, cin = _act(x).shape
+    cout = w_bf16.shape[0]
+    y = torch.empty(n, h, w, cout, dtype=BF16, device=x.device)
+    partial = torch.empty(max(lib.cmu_conv_max_grid(), 64) * 2 * max(128, cout), dtype=torch.float32, device=x.device)
+    g, b = ctypes.c_int(0), ctypes.c_int(0)
+    with _timed(name, 2.0 * n * h * w * cin * cout):
+        lib.cmu_conv1x1_fprop_exp(_ptr(x), cin, n, h, w, _ptr(w_bf16), cout, float(inv_temperature), _ptr(y), _ptr(partial),
+                                  ctypes.byref(g), ctypes.byref(b), _stream())
+    return y, partial, g.value, b.value
+
+
 def head1x1_fprop(a, w, b):
     """a act (N,H,W,64); w (2,64[,1,1]) fp32; -> (N,2,H,W) fp32 NCHW."""
     n, h, wd, cin = _act(a).shape

@@ -33,7 +33,9 @@ int cmu_debug_set(int key, int value);    /* 0: 1 = CUDA-core cross-check path f
                                              64-channel wgrad; 9: 1 = one epilogue warp group; 10: 1 = wgrad CTAs of one
                                              pixel range launched as a paced cluster (A/B, profiles/r1_k2_dram_traffic.md);
                                              11: 1 = ConvTranspose on the 1-CTA kernel (A/B); 12: 1 = full-depth TMA ring for
-                                             one-tile wgrad CTAs (A/B) */
+                                             one-tile wgrad CTAs (A/B); 13: unused; 14: KB of shared
+                                             memory the K1 kernels leave free per SM, 15: 2 = two-stage K2 ring (A/B:
+                                             co-residency of HBM-bound kernels of other streams) */
 
 /* ---- a1  patch-mask generator: CMU/backbones/UNet_encoder.py:106-139 (create_random_patch_mask) ------------
  * d_state: uint32[cmu_mask_state_words()] = MT19937 key[624] + position, same content as numpy's
@@ -157,6 +159,15 @@ int cmu_moco_softmax(const void* lt /* bf16 [K][N] */, const float* lpos, int k,
                      float* loss_rows, float* loss, float* ppos, void* p /* bf16 [K][N] or NULL */, void* stream);
 int cmu_moco_dq(const float* dq_neg, const float* k, const float* qh, const float* qnorm, const float* ppos, int n, int d,
                 float temperature, float* dq, void* stream);
+/* fused form (the one Moco_v2 uses): logits never reach HBM.  cmu_conv1x1_fprop_exp stores E[k][n] = exp((Queue_k . q_n - 1)/T)
+ * (bf16, the operand of the backward GEMM dq = E^T Queue) and per-CTA partial column sums; cmu_moco_finish turns them into
+ * the loss, the probability of the positive and the per-query scale 1/(Z N T); cmu_moco_dq_scaled applies that scale. */
+int cmu_conv1x1_fprop_exp(const void* x, int cin, int n, int h, int w, const void* w_packed, int cout, float inv_temperature,
+                          void* y, float* sums_partial, int* sums_grid, int* sums_bn, void* stream);
+int cmu_moco_finish(const float* sums_partial, int sums_grid, int sums_bn, int n, const float* lpos, float temperature,
+                    float* loss_rows, float* loss, float* ppos, float* row_scale, void* stream);
+int cmu_moco_dq_scaled(const float* dq_neg_unnorm, const float* row_scale, const float* k, const float* qh,
+                       const float* qnorm, const float* ppos, int n, int d, float temperature, float* dq, void* stream);
 int cmu_queue_enqueue(const float* keys, int n, int d, int k, int ptr, void* queue_rows /* bf16 [K][D] */,
                       float* queue_ref /* fp32 (D,K) reference layout or NULL */, void* stream);
 

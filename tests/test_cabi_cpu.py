@@ -198,3 +198,51 @@ def test_data_pipeline_host_draws_match_the_oracle_order():
     if not torch.cuda.is_available():
         with pytest.raises(C.CmuError):
             pipe(torch.zeros(1, 64, 64, dtype=torch.uint8), pipe.draw_params(1))
+
+
+def test_checkpoint_handoff_moco_to_finetune(tmp_path):
+    """Finetuning/train.py:286-296 (".ckpt" branch): a MoCo-v2 checkpoint hands its QUERY encoder to the fine-tune UNet
+    (`encoder_q.` stripped, `encoder_k.*` ignored); a checkpoint with no usable encoder tensor raises instead of silently
+    fine-tuning from random weights."""
+    from contrastive_masked_unet_b200.checkpoint import (finetune_state_dict, load_pretrained_into_unet,
+                                                         save_moco_checkpoint)
+    torch.manual_seed(9)
+    m = C.Moco_v2(emb_dim=1024, num_negatives=128)
+    with torch.no_grad():                       # make the two encoders differ so that a mix-up would show
+        for p in m.encoder_k.parameters():
+            p.add_(1.0)
+    path = str(tmp_path / 'moco_epoch_3.ckpt')
+    ck = save_moco_checkpoint(m, path, epoch=3)
+    assert any(k.startswith('encoder_q.') for k in ck['state_dict']) and 'queue' in ck['state_dict']
+    mapped = finetune_state_dict(ck, path)
+    assert all(not k.startswith('encoder_') for k in mapped) and 'down_conv1.double_conv.double_conv.0.weight' in mapped
+    torch.manual_seed(10)
+    u = C.UNet()
+    up_w = u.up_conv3.up_sample.weight.detach().clone()
+    res = load_pretrained_into_unet(u, path)
+    assert torch.equal(u.down_conv2.double_conv.double_conv[3].weight, m.encoder_q.down_conv2.double_conv.double_conv[3].weight)
+    assert not torch.equal(u.down_conv2.double_conv.double_conv[3].weight, m.encoder_k.down_conv2.double_conv.double_conv[3].weight)
+    assert torch.equal(u.up_conv3.up_sample.weight, up_w)                       # decoder untouched: encoder-only hand-off
+    assert all(k.startswith(('up_conv', 'conv_last')) for k in res.missing_keys)
+    # detection by key prefix when the extension is not .ckpt (this package's own state_dict)
+    res2 = load_pretrained_into_unet(C.UNet(), {'state_dict': m.state_dict()})
+    assert all(k.startswith(('up_conv', 'conv_last')) for k in res2.missing_keys)
+    # the same file loads in the oracle (== reference layout) UNet
+    load_pretrained_into_unet(O.OracleUNet(), path)
+    # nothing usable -> loud failure
+    with pytest.raises(ValueError, match='no tensor for any encoder key'):
+        load_pretrained_into_unet(C.UNet(), {'state_dict': {'encoder_x.down_conv1.weight': torch.zeros(1), 'foo.bar': torch.zeros(1)}})
+
+
+def test_moco_queue_cache_signature_follows_buffer_writes():
+    """The bf16 working copy of the MoCo queue is keyed on the buffers' version counters: load_state_dict / in-place
+    writes invalidate it, the module's own bookkeeping does not."""
+    torch.manual_seed(1)
+    m = C.Moco_v2(emb_dim=1024, num_negatives=256)
+    s0 = m._queue_sig()
+    m.queue_ptr[0] = 64
+    assert m._queue_sig() != s0
+    s1 = m._queue_sig()
+    m.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})
+    assert m._queue_sig() != s1
+    assert m.shuffle_bn is True

@@ -20,6 +20,11 @@ def test_two_rank_ddp_matches_oracle():
     line = [l for l in r.stdout.splitlines() if l.startswith('DIST_RESULT ')]
     assert line, (r.stdout[-2000:], r.stderr[-2000:])
     res = json.loads(line[0][len('DIST_RESULT '):])
+    check_dist_result(res)
+
+
+def check_dist_result(res):
+    """pass/fail bars of the 2-rank worker report (shared with __graft_entry__.smoke)."""
     for rr in res:
         for k, tol in (('loss_ct', 1.5e-2), ('loss_rc', 1e-2)):   # loss_ct: SyncBN over only 32 rows (see model_checks)
             a, b = rr[k]

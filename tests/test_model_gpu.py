@@ -183,3 +183,30 @@ def test_frozen_bn_conv_bias_gets_its_gradient():
         gw, gwr = dc.double_conv[i].weight.grad, ref.double_conv[i].weight.grad
         # fp32 inputs are quantised to bf16 at the module boundary (same bar as test_standalone_blocks_accept_fp32_nchw)
         assert cos(gw.flatten(), gwr.flatten(), dim=0) > 0.995
+
+
+def test_moco_resume_from_state_dict_uses_loaded_queue_and_pointer():
+    """step, save, step, load the saved state, step again: the second model continues exactly like a fresh model that
+    loaded the same state (queue contents, pointer, bf16 working copy) -- ADVICE r1, moco.py `_queue_rows` cache."""
+    _gpu()
+    import contrastive_masked_unet_b200 as C
+    torch.manual_seed(3)
+    m = C.Moco_v2(emb_dim=1024, num_negatives=512).cuda().train()
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.rand(64, 32, 32, generator=g).cuda(), torch.rand(64, 32, 32, generator=g).cuda()) for _ in range(3)]
+    m.training_step(*batches[0]).backward()
+    saved = {k: v.clone() for k, v in m.state_dict().items()}
+    m.training_step(*batches[1]).backward()                 # moves the pointer and the cached rows past the saved state
+    assert int(m.queue_ptr) == 128
+    m.load_state_dict(saved)                                # resume
+    assert int(m.queue_ptr) == 64
+    loss_a = m.training_step(*batches[2])
+    torch.manual_seed(3)
+    fresh = C.Moco_v2(emb_dim=1024, num_negatives=512).cuda().train()
+    fresh.load_state_dict(saved)
+    loss_b = fresh.training_step(*batches[2])
+    torch.cuda.synchronize()
+    assert float(loss_a) == float(loss_b), (float(loss_a), float(loss_b))
+    assert int(m.queue_ptr) == int(fresh.queue_ptr) == 128
+    assert torch.equal(m.queue, fresh.queue) and torch.equal(m._rows, fresh._rows)
+    assert float((m._rows.float() - m.queue.t()).abs().max()) < 1e-2
