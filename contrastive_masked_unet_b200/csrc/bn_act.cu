@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool_kernel(const __nv_bfloat16* 
         f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
       }
       const uint4 pk = pack8(f);
-      reinterpret_cast<uint4*>(a)[pix * cgs + cg] = pk;
+      if (a != nullptr) reinterpret_cast<uint4*>(a)[pix * cgs + cg] = pk;   // a == nullptr: only the pooled map is wanted
       float fr[8];
       unpack8(pk, fr);  // pool the bf16-rounded values (what consumers of `a` see)
 #pragma unroll

@@ -35,11 +35,14 @@ def _nchw_view(a):
 
 
 class BNConfig:
-    __slots__ = ('training', 'momentum', 'eps', 'pool', 'grad')
+    __slots__ = ('training', 'momentum', 'eps', 'pool', 'grad', 'want_act')
 
-    def __init__(self, training, momentum, eps, pool):
+    def __init__(self, training, momentum, eps, pool, want_act=True):
         self.training, self.momentum, self.eps, self.pool = training, momentum, eps, pool
         self.grad = torch.is_grad_enabled()     # captured at call time (grad mode is always off inside Function.forward)
+        # pooled layers whose full-resolution activation (the skip tensor) nobody reads: skip its store (backward
+        # recomputes ReLU mask and pool routing from y, so the tensor is not needed for autograd either)
+        self.want_act = want_act or not pool
 
 
 def _conv_bias_grad(dy, bn_training):
@@ -64,14 +67,14 @@ class ConvBNReLUFn(torch.autograd.Function):
         y, stats = ops.conv3x3_fprop(a0, a1, wf, want_stats=cfg.training)
         scale, shift, mean, rstd = ops.bn_finalize(stats, gamma, beta, bias, running_mean, running_var, cfg.momentum,
                                                    cfg.eps, cfg.training)
-        act, pooled = ops.bn_relu_apply(y, scale, shift, cfg.pool)
+        act, pooled = ops.bn_relu_apply(y, scale, shift, cfg.pool, cfg.want_act)
         if need_grad:
             ctx.save_for_backward(a0, a1, y, scale, shift, mean, rstd, wd)
             ctx.c0 = a0.shape[3]
             ctx.c1 = 0 if a1 is None else a1.shape[3]
         ctx.pool, ctx.bn_training = cfg.pool, cfg.training
         if cfg.pool:
-            return _nchw_view(act), _nchw_view(pooled)
+            return (_nchw_view(act) if act is not None else None), _nchw_view(pooled)
         return _nchw_view(act)
 
     @staticmethod

@@ -101,10 +101,10 @@ class MocoUNetEncoder(nn.Module):
     def forward(self, x):
         if x.dim() == 3:
             x = x.unsqueeze(1)
-        x, _ = self.down_conv1(x)
-        x, _ = self.down_conv2(x)
-        x, _ = self.down_conv3(x)
-        x, _ = self.down_conv4(x)
+        x, _ = self.down_conv1(x, want_skip=False)      # the skip tensors have no consumer here: never stored
+        x, _ = self.down_conv2(x, want_skip=False)
+        x, _ = self.down_conv3(x, want_skip=False)
+        x, _ = self.down_conv4(x, want_skip=False)
         x = self.double_conv(x)
         return SpatialMeanFn.apply(Fn.to_act(x))
 

@@ -178,16 +178,16 @@ class MaskStream:
 
 
 # --------------------------------------------------------------------------------------------------------- conv blocks
-def _bn_cfg(bn, pool):
+def _bn_cfg(bn, pool, want_act=True):
     mom = bn.momentum if bn.momentum is not None else 0.1
-    return Fn.BNConfig(bn.training, mom, bn.eps, pool)
+    return Fn.BNConfig(bn.training, mom, bn.eps, pool, want_act)
 
 
-def _conv_bn_relu(conv, bn, x0, x1=None, pool=False):
+def _conv_bn_relu(conv, bn, x0, x1=None, pool=False, want_act=True):
     if bn.training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     return Fn.ConvBNReLUFn.apply(Fn.to_act(x0), None if x1 is None else Fn.to_act(x1), conv.weight, conv.bias, bn.weight,
-                                 bn.bias, bn.running_mean, bn.running_var, _bn_cfg(bn, pool))
+                                 bn.bias, bn.running_mean, bn.running_var, _bn_cfg(bn, pool, want_act))
 
 
 @register
@@ -203,7 +203,7 @@ class DoubleConv(nn.Module):
             nn.ReLU(inplace=True))
         self.in_channels, self.out_channels = in_channels, out_channels
 
-    def run(self, x, skip=None, mask=None, pool=False):
+    def run(self, x, skip=None, mask=None, pool=False, want_skip=True):
         """x: NCHW-shaped tensor (fp32 (N,1,H,W) for the first layer); skip: second concat source; mask: (B,H,W) uint8
         whose image 0 masks the whole batch (first layer only)."""
         seq = self.double_conv
@@ -219,7 +219,7 @@ class DoubleConv(nn.Module):
             if mask is not None:
                 raise CmuError('input masking is fused into the 1-channel first layer only')
             a = _conv_bn_relu(seq[0], seq[1], x, skip, False)
-        return _conv_bn_relu(seq[3], seq[4], a, None, pool)
+        return _conv_bn_relu(seq[3], seq[4], a, None, pool, want_skip)
 
     def forward(self, x):
         return self.run(x)
@@ -234,8 +234,10 @@ class DownBlock(nn.Module):
         self.double_conv = DoubleConv(in_channels, out_channels)
         self.down_sample = nn.MaxPool2d(2)
 
-    def forward(self, x, mask=None):
-        skip_out, down_out = self.double_conv.run(x, mask=mask, pool=True)
+    def forward(self, x, mask=None, want_skip=True):
+        """want_skip=False: the full-resolution skip tensor is not written and comes back as None (the frozen target
+        encoder of CM_UNet and the MoCo encoders only use the pooled path; backward does not need the tensor)."""
+        skip_out, down_out = self.double_conv.run(x, mask=mask, pool=True, want_skip=want_skip)
         return (down_out, skip_out)
 
 
@@ -295,15 +297,17 @@ class UNet_encoder(nn.Module):
         self.mask_ratio = mask_ratio
         self.mask_stream = MaskStream()
 
-    def forward(self, x):
+    def forward(self, x, want_skips=True):
+        """want_skips=False: a caller that only uses the latent (CM_UNet's frozen target path, under no_grad) lets the
+        encoder skip the four full-resolution skip stores; the list then holds None entries."""
         ops._need_cuda(x)
         b, s = x.shape[0], x.shape[1]
         mask, k = self.mask_stream.generate(b, s, self.patch_size, self.mask_ratio, x.device)
         x = x.unsqueeze(1)
-        x, skip1_out = self.down_conv1(x, mask=mask if k > 0 else None)     # fused x * (1 - mask[0])  (:156, Q1)
-        x, skip2_out = self.down_conv2(x)
-        x, skip3_out = self.down_conv3(x)
-        x, skip4_out = self.down_conv4(x)
+        x, skip1_out = self.down_conv1(x, mask=mask if k > 0 else None, want_skip=want_skips)   # fused x * (1 - mask[0])  (:156, Q1)
+        x, skip2_out = self.down_conv2(x, want_skip=want_skips)
+        x, skip3_out = self.down_conv3(x, want_skip=want_skips)
+        x, skip4_out = self.down_conv4(x, want_skip=want_skips)
         x = self.double_conv(x)
         return x, mask, [skip1_out, skip2_out, skip3_out, skip4_out]
 
@@ -552,7 +556,7 @@ class CM_UNet(nn.Module):
 
     def _target_branch(self, img, img_t):
         """Frozen target path (no grad): target encoder -> fresh 1x1 reduce (Q3) -> NCHW flatten -> target projector."""
-        latent_t, _, _ = self.target_backbone(img_t)
+        latent_t, _, _ = self.target_backbone(img_t, want_skips=False)
         rw, rb = self._reduce_params(img.device)
         lt = ops.conv1x1_fprop(Fn._nhwc(Fn.to_act(latent_t)), rw, rb)          # (B,h,w,256) act
         b, h, w, c = lt.shape

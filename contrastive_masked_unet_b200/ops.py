@@ -223,9 +223,10 @@ def bn_finalize(stats, gamma, beta, conv_bias, running_mean, running_var, moment
     return out[0], out[1], out[2], out[3]
 
 
-def bn_relu_apply(y, scale, shift, pool=False):
+def bn_relu_apply(y, scale, shift, pool=False, want_act=True):
+    """want_act=False (with pool=True): only the pooled map is written (no-grad paths whose skip tensor nobody reads)."""
     n, h, w, c = _act(y).shape
-    a = torch.empty_like(y)
+    a = torch.empty_like(y) if (want_act or not pool) else None
     pooled = torch.empty(n, h // 2, w // 2, c, dtype=BF16, device=y.device) if pool else None
     lib.cmu_bn_relu_apply(_ptr(y), _ptr(scale), _ptr(shift), _ptr(a), _ptr(pooled), n, h, w, c, _stream())
     return a, pooled

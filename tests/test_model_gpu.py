@@ -206,7 +206,11 @@ def test_moco_resume_from_state_dict_uses_loaded_queue_and_pointer():
     fresh.load_state_dict(saved)
     loss_b = fresh.training_step(*batches[2])
     torch.cuda.synchronize()
-    assert float(loss_a) == float(loss_b), (float(loss_a), float(loss_b))
+    # (the conv statistics use shared-memory float atomics: two runs agree to rounding, not to the bit)
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-4 * abs(float(loss_b)), (float(loss_a), float(loss_b))
     assert int(m.queue_ptr) == int(fresh.queue_ptr) == 128
-    assert torch.equal(m.queue, fresh.queue) and torch.equal(m._rows, fresh._rows)
+    assert torch.equal(m.queue[:, 128:], fresh.queue[:, 128:]) and torch.equal(m.queue[:, 128:], saved['queue'][:, 128:])
+    assert float((m.queue[:, :128] - fresh.queue[:, :128]).abs().max()) < 2e-2      # keys of a bf16 encoder
     assert float((m._rows.float() - m.queue.t()).abs().max()) < 1e-2
+    # without the cache invalidation the stale rows / pointer would have been used: the step-2 keys sit in columns 64..127
+    assert not torch.equal(saved['queue'][:, 64:128], m.queue[:, 64:128])
