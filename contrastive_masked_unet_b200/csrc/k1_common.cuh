@@ -33,6 +33,7 @@ struct K1Params {
   const float* bias;
   int bias_mod;
   float* stats;     // [gridDim.x][2][BN] partial (sum, sum of squares) or nullptr
+  int single_patch; // conv3 pair kernel: ONE haloed (TH+2) x (TW+2) patch per K chunk, the 9 taps are descriptor offsets
   float exp_scale;  // != 0: epilogue stores exp((acc - 1) * exp_scale) (MoCo queue logits -> unnormalised softmax terms)
 };
 
@@ -78,6 +79,7 @@ __device__ __forceinline__ void slab_stats(const uint8_t* warp_stg, uint32_t lan
 
 
 // pair kernel (tc_conv2.cu): returns 0 on success; *used = 1 if the launch was taken by the pair kernel
-int run_k1_pair(K1Params& p, const void* wpk, int ktot, cudaStream_t stream, int* used_grid, int* used_bn);
+int run_k1_pair(K1Params& p, const void* a0, const void* a1, const void* wpk, int ktot, cudaStream_t stream,
+                int* used_grid, int* used_bn);
 
 }  // namespace cmu

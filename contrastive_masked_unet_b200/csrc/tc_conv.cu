@@ -476,7 +476,7 @@ static int run_k1(int mode, const void* a0, int c0, const void* a1, int c1, int 
   {
     int pair_grid = 0, pair_bn = 0;
     K1Params pp = p;
-    if (run_k1_pair(pp, wpk, ktot, stream, &pair_grid, &pair_bn)) return 1;
+    if (run_k1_pair(pp, a0, a1, wpk, ktot, stream, &pair_grid, &pair_bn)) return 1;
     if (pair_grid > 0) {
       if (stats_grid) *stats_grid = pair_grid;
       if (stats_bn) *stats_bn = pair_bn;

@@ -89,7 +89,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
   const int sup0 = cid / p.n_tiles;
   const int sup_stride = n_clusters / p.n_tiles;
   const int n_super = (p.m_tiles + 1) >> 1;
-  const int shifts = (p.mode == MODE_CONV3) ? 3 : 1;
+  const int shifts = (p.mode == MODE_CONV3 && !p.single_patch) ? 3 : 1;   // pipeline stages per K chunk
   const int kc = p.kc;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
@@ -103,7 +103,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
         for (int c = 0; c < kc; ++c)
           for (int s = 0; s < shifts; ++s)
             tma_load_3d_pair(w_res + (c * shifts + s) * p.b_bytes, &p.tmB, wb, c << 6, n0 + (int)rank * kHalfN,
-                             (p.mode == MODE_CONV3) ? 3 * s : 0);
+                             (p.mode == MODE_CONV3) ? 3 * s : 0);   // single_patch: one box holds all 9 taps (s = 0)
       }
       uint32_t it = 0;
       for (int sup = sup0; sup < n_super; sup += sup_stride) {
@@ -131,8 +131,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
               const bool second = k0 >= p.c0;
               const CUtensorMap* src = second ? &p.tmA1 : &p.tmA0;
               const int cc = second ? k0 - p.c0 : k0;
-              if (p.mode == MODE_CONV3)
-                tma_load_4d_pair(sA, src, fb, cc, w0 + s - 1, h0 - 1, img);
+              if (p.mode == MODE_CONV3)   // single_patch: box (TW+2) x (TH+2) at (w0-1, h0-1); else column-shifted copies
+                tma_load_4d_pair(sA, src, fb, cc, w0 + (p.single_patch ? 0 : s) - 1, h0 - 1, img);
               else
                 tma_load_4d_pair(sA, src, fb, cc, w0, h0, img);
             }
@@ -151,6 +151,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
       const bool conv3 = (p.mode == MODE_CONV3);
       const uint32_t stage0 = smem_u32(stage_base);
       const uint64_t desc_hi = umma_smem_desc(0, 16, 1024);
+      // single-patch mode: the tile's 8-pixel row groups sit (TW+2) pixel rows apart inside the haloed patch
+      const uint64_t desc_hi_sp = umma_smem_desc(0, 16, (uint32_t)(p.TW + 2) * 128u);
+      const bool single_patch = p.single_patch != 0;
+      const uint32_t pitch16 = ((uint32_t)(p.TW + 2) * 128u) >> 4;   // patch row pitch in 16-byte units
       uint32_t it = 0, tile_it = 0;
       const uint32_t w_base = smem_u32(w_res);
       if (p.w_resident) mbar_wait(wfull_bar, 0);
@@ -168,10 +172,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
           tc_fence_after();
           const uint32_t sA = stage0 + st * p.stage_bytes;
           const uint32_t sB = p.w_resident ? w_base + sidx * p.b_bytes : sA + p.b_off;   // sidx = c * shifts + s
-          const uint64_t a0 = desc_hi | (uint64_t)((sA >> 4) & 0x3FFF);
+          const uint64_t a0 = (single_patch ? desc_hi_sp : desc_hi) | (uint64_t)((sA >> 4) & 0x3FFF);
           const uint64_t b0 = desc_hi | (uint64_t)((sB >> 4) & 0x3FFF);
           if (elect_one()) {
-            if (conv3) {
+            if (conv3 && single_patch) {
+              // tap (s, r): A starts (r * (TW+2) + s) pixel rows into the patch, B at weight tap 3 s + r
+#pragma unroll
+              for (int s = 0; s < 3; ++s) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16_pair(d_tmem, a0 + (uint64_t)(r * pitch16 + s * 8 + k * 2),
+                                   b0 + (uint64_t)((3 * s + r) * (kHalfN * 8) + k * 2), idesc, (sidx | s | r | k) != 0 ? 1u : 0u);
+                }
+              }
+            } else if (conv3) {
 #pragma unroll
               for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -309,7 +325,8 @@ static int launch_pair(const K1Params& p, int grid, int smem_bytes, cudaStream_t
 
 // Takes the launch when the pair kernel applies (conv3x3 / plain modes, GEMM-N multiple of 128, enough tiles).
 // `p` arrives fully prepared for the 1-CTA kernel; tile maps are re-encoded where the box differs (weight half tiles).
-int run_k1_pair(K1Params& p, const void* wpk, int ktot, cudaStream_t stream, int* used, int* used_bn) {
+int run_k1_pair(K1Params& p, const void* a0, const void* a1, const void* wpk, int ktot, cudaStream_t stream, int* used,
+                int* used_bn) {
   *used = 0;
   if (debug_knob(5) == 1) return 0;
   const bool convT = (p.mode == MODE_CONVT_FPROP || p.mode == MODE_CONVT_DGRAD);
@@ -323,11 +340,31 @@ int run_k1_pair(K1Params& p, const void* wpk, int ktot, cudaStream_t stream, int
     const int taps = (p.mode == MODE_CONV3) ? 9 : 1;
     uint64_t dims[3] = {(uint64_t)ktot, (uint64_t)p.n_total, (uint64_t)taps};
     uint64_t str[2] = {(uint64_t)ktot * 2, (uint64_t)p.n_total * ktot * 2};
-    uint32_t box[3] = {64, (uint32_t)(BN / 2), (uint32_t)((p.mode == MODE_CONV3) ? 3 : 1)};
+    const bool sp = (p.mode == MODE_CONV3 && p.TW == 8 && BN == 64 && debug_knob(13) != 1);
+    uint32_t box[3] = {64, (uint32_t)(BN / 2), (uint32_t)((p.mode == MODE_CONV3) ? (sp ? 9 : 3) : 1)};
     if (encode_tmap_bf16(&p.tmB, wpk, 3, dims, str, box)) return 1;
   }
-  p.a_bytes = (p.mode == MODE_CONV3) ? (p.TH + 2) * p.TW * 128 : 128 * 128;
-  p.b_bytes = ((p.mode == MODE_CONV3) ? 3 : 1) * (BN / 2) * 128;
+  // single-patch staging (conv3x3, 8-wide tiles, N = 64 tiles -- the shared-memory-bound layers): one haloed patch per K
+  // chunk instead of three column-shifted copies; the nine taps become start-address offsets of the UMMA descriptor
+  // (row pitch (TW+2) x 128 B: the hardware applies the 128-byte swizzle to the absolute shared-memory address, so
+  // starts that are not 1024-byte aligned read what TMA wrote).  Wider n-tiles keep the three-copy scheme: their nine-
+  // tap weight stage (9 x BN/2 x 128 B) would leave no room for a pipeline.  Knob 13 = 1: off (A/B).
+  p.single_patch = (p.mode == MODE_CONV3 && p.TW == 8 && BN == 64 && debug_knob(13) != 1) ? 1 : 0;
+  if (p.single_patch) {   // activation maps with the haloed (TW+2) x (TH+2) box
+    const void* srcs[2] = {a0, a1};
+    const int chans[2] = {p.c0, p.c1};
+    CUtensorMap* maps[2] = {&p.tmA0, &p.tmA1};
+    for (int i = 0; i < 2; ++i) {
+      if (srcs[i] == nullptr) continue;
+      uint64_t dims[4] = {(uint64_t)chans[i], (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.N};
+      uint64_t str[3] = {(uint64_t)chans[i] * 2, (uint64_t)p.W * chans[i] * 2, (uint64_t)p.H * p.W * chans[i] * 2};
+      uint32_t box[4] = {64, (uint32_t)(p.TW + 2), (uint32_t)(p.TH + 2), 1};
+      if (encode_tmap_bf16(maps[i], srcs[i], 4, dims, str, box)) return 1;
+    }
+    if (a1 == nullptr) p.tmA1 = p.tmA0;
+  }
+  p.a_bytes = (p.mode == MODE_CONV3) ? (p.TH + 2) * (p.single_patch ? p.TW + 2 : p.TW) * 128 : 128 * 128;
+  p.b_bytes = ((p.mode == MODE_CONV3) ? (p.single_patch ? 9 : 3) : 1) * (BN / 2) * 128;
   p.b_off = (p.a_bytes + 1023) & ~1023;
   p.stage_bytes = p.b_off + p.b_bytes;
   p.w_resident = 0;
@@ -337,7 +374,7 @@ int run_k1_pair(K1Params& p, const void* wpk, int ktot, cudaStream_t stream, int
   // small-weight layers (64-wide n-tiles): keep this CTA's half of the weights resident for the whole persistent loop and
   // stream activations only -- 40 % less TMA fill per tile and a deeper activation pipeline (these layers have 1-2 K
   // chunks per tile, so the TMA latency is hidden by the number of stages in flight, not by the length of a tile)
-  const int w_all = p.kc * ((p.mode == MODE_CONV3) ? 3 : 1) * p.b_bytes;
+  const int w_all = p.kc * ((p.mode == MODE_CONV3 && !p.single_patch) ? 3 : 1) * p.b_bytes;
   if (debug_knob(4) != 1 && BN == 64 && w_all <= 80 * 1024 &&
       (smem_budget() - fixed - 2 * kStagingBytes - w_all) / p.b_off >= 5) {
     p.w_resident = 1;
