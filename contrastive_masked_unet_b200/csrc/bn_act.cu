@@ -342,6 +342,28 @@ __global__ void __launch_bounds__(256) reduce_rows_kernel(const float* __restric
   }
 }
 
+// out[c] = sum over CTAs of the SUM half of conv-epilogue statistics: partial[grid][2][bn_tile], the CTA with index b owns
+// channel tile (b % n_tiles).  Used for the ConvTranspose bias gradient (= per-channel sum of the dgrad output).
+__global__ void __launch_bounds__(256) stats_colsum_kernel(const float* __restrict__ partial, int grid, int bn, int n_tiles,
+                                                           int c_count, float* __restrict__ out) {
+  __shared__ double sred[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double a = 0.0;
+  if (c < c_count) {
+    const int nt = c / bn, cc = c - nt * bn;
+    for (int r = nt + ry * n_tiles; r < grid; r += 8 * n_tiles) a += partial[((size_t)r * 2) * bn + cc];
+  }
+  sred[ry][cx] = a;
+  __syncthreads();
+  if (ry == 0 && c < c_count) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sred[k][cx];
+    out[c] = (float)t;
+  }
+}
+
 // ---------------------------------------------------------------------------------- BN finalize
 // partial layout: [grid][2][bn_tile]; the CTA with index b owns channel tile (b % n_tiles).
 // Train: mean/var from the batch (biased var for normalisation, unbiased for running_var); the conv bias is not
@@ -807,6 +829,15 @@ int cmu_colsum_bf16(const void* x, long long rows, int c, float* partial, float*
                                                                             partial);
   CMU_LAUNCH_CHECK();
   reduce_rows_kernel<<<ceil_div(c, 32), 256, 0, (cudaStream_t)stream>>>(partial, out, grid, c, 0);
+  CMU_LAUNCH_CHECK();
+  return 0;
+}
+
+int cmu_stats_colsum(const float* partial, int grid, int bn_tile, int c_total, int c_count, float* out, void* stream) {
+  CMU_REQUIRE(partial != nullptr && grid > 0 && bn_tile > 0 && c_total % bn_tile == 0 && c_count <= c_total,
+              "stats_colsum: bad partial layout");
+  stats_colsum_kernel<<<ceil_div(c_count, 32), 256, 0, (cudaStream_t)stream>>>(partial, grid, bn_tile, c_total / bn_tile,
+                                                                              c_count, out);
   CMU_LAUNCH_CHECK();
   return 0;
 }

@@ -536,6 +536,14 @@ int cmu_conv3x3_dgrad(const void* dy, int cout, int n, int h, int w, const void*
                 nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
+// dgrad with the per-CTA column sums of its bf16 outputs (same partial layout as the fprop statistics): the sum over
+// the first c0 output channels is the bias gradient of the ConvTranspose2d that produced x0 (munet_neck.py:46-49).
+int cmu_conv3x3_dgrad_sums(const void* dy, int cout, int n, int h, int w, const void* w_packed_dgrad, void* dx0, int c0,
+                           void* dx1, int c1, float* sums_partial, int* sums_grid, int* sums_bn, void* stream) {
+  return run_k1(MODE_CONV3, dy, cout, nullptr, 0, n, h, w, w_packed_dgrad, c0 + c1, dx0, c0, dx1, c1, nullptr, 0,
+                sums_partial, sums_grid, sums_bn, (cudaStream_t)stream);
+}
+
 int cmu_conv1x1_fprop(const void* x, int cin, int n, int h, int w, const void* w_packed, int cout, const float* bias,
                       void* y, void* stream) {
   return run_k1(MODE_PLAIN, x, cin, nullptr, 0, n, h, w, w_packed, cout, y, cout, nullptr, 0, bias, cout, nullptr,

@@ -152,15 +152,26 @@ def conv3x3_fprop(x0, x1, wf, want_stats=True):
     return y, stats
 
 
-def conv3x3_dgrad(dy, wd, c0, c1=0):
+def conv3x3_dgrad(dy, wd, c0, c1=0, want_colsum0=False):
+    """-> (dx0, dx1) [, colsum0]: with want_colsum0 the per-channel sum of dx0 over all pixels (fp32 (c0,), taken in the
+    epilogue from the stored bf16 values) is returned as well -- the bias gradient of a ConvTranspose2d that produced x0."""
     _need_cuda(dy, wd)
     _act(dy)
     n, h, w, cout = dy.shape
     dx0 = torch.empty(n, h, w, c0, dtype=BF16, device=dy.device)
     dx1 = torch.empty(n, h, w, c1, dtype=BF16, device=dy.device) if c1 else None
+    if not want_colsum0:
+        with _timed('conv3x3_dgrad', 2.0 * n * h * w * cout * 9 * (c0 + c1)):
+            lib.cmu_conv3x3_dgrad(_ptr(dy), cout, n, h, w, _ptr(wd), _ptr(dx0), c0, _ptr(dx1), c1, _stream())
+        return dx0, dx1
+    partial = torch.empty(max(lib.cmu_conv_max_grid(), 64) * 2 * max(128, c0 + c1), dtype=torch.float32, device=dy.device)
+    g, b = ctypes.c_int(0), ctypes.c_int(0)
     with _timed('conv3x3_dgrad', 2.0 * n * h * w * cout * 9 * (c0 + c1)):
-        lib.cmu_conv3x3_dgrad(_ptr(dy), cout, n, h, w, _ptr(wd), _ptr(dx0), c0, _ptr(dx1), c1, _stream())
-    return dx0, dx1
+        lib.cmu_conv3x3_dgrad_sums(_ptr(dy), cout, n, h, w, _ptr(wd), _ptr(dx0), c0, _ptr(dx1), c1, _ptr(partial),
+                                   ctypes.byref(g), ctypes.byref(b), _stream())
+    colsum0 = torch.empty(c0, dtype=torch.float32, device=dy.device)
+    lib.cmu_stats_colsum(_ptr(partial), g.value, b.value, c0 + c1, c0, _ptr(colsum0), _stream())
+    return dx0, dx1, colsum0
 
 
 def conv3x3_wgrad(x0, x1, dy, dw=None, accumulate=False):

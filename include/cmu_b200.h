@@ -68,12 +68,21 @@ int cmu_conv3x3_c1_wgrad(const float* x, const unsigned char* mask0, const void*
 /* conv3x3 pad 1 as tcgen05 implicit GEMM.  (x0|x1) = channel concat of two act tensors (munet_neck.py:48; x1 may be
  * NULL).  The conv bias is NOT applied (it cancels inside the train-mode BN that always follows; cmu_bn_finalize
  * folds it into running_mean / the eval shift).  stats_partial: float[*stats_grid][2][*stats_bn] per-CTA
- * (sum, sumsq) of the fp32 accumulators; size it with cmu_conv_max_grid() * 2 * max(128, Cout). */
+ * (sum, sumsq), accumulated in fp32 over the bf16-ROUNDED outputs -- exactly the values y that BatchNorm later
+ * normalises (torch's batch_norm also takes its statistics from the stored tensor); they differ from statistics of the
+ * fp32 accumulators by the rounding noise only (<= 2e-3 relative on sumsq, tests/kernel_checks.py stats_sq_vs_fp32);
+ * cmu_bn_finalize reduces the partial rows in fp64.  Size it with cmu_conv_max_grid() * 2 * max(128, Cout). */
 int cmu_conv_max_grid(void);
 int cmu_conv3x3_fprop(const void* x0, int c0, const void* x1, int c1, int n, int h, int w, const void* w_packed, int cout,
                       void* y, float* stats_partial, int* h_stats_grid, int* h_stats_bn, void* stream);
 int cmu_conv3x3_dgrad(const void* dy, int cout, int n, int h, int w, const void* w_packed_dgrad, void* dx0, int c0,
                       void* dx1, int c1, void* stream);
+/* dgrad that also delivers per-CTA column sums of its outputs (partial layout as stats_partial above); cmu_stats_colsum
+ * reduces the SUM half over the CTAs for the first c_count channels: the bias gradient of the ConvTranspose2d whose
+ * output was x0 (munet_neck.py:46-49) without a separate pass over dx0. */
+int cmu_conv3x3_dgrad_sums(const void* dy, int cout, int n, int h, int w, const void* w_packed_dgrad, void* dx0, int c0,
+                           void* dx1, int c1, float* sums_partial, int* h_sums_grid, int* h_sums_bn, void* stream);
+int cmu_stats_colsum(const float* partial, int grid, int bn_tile, int c_total, int c_count, float* out, void* stream);
 long long cmu_conv3x3_wgrad_workspace_bytes(int cin, int cout, int n, int h, int w);
 int cmu_conv3x3_wgrad(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout, int n, int h, int w,
                       float* workspace, long long workspace_bytes, float* dw /* (Cout,Cin,3,3) fp32 */, int accumulate,

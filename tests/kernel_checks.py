@@ -73,9 +73,13 @@ def check_conv3x3(n=2, h=24, w=40, c0=64, c1=0, cout=64, seed=0, tol=1.5e-2):
     yr.backward(nchw(dy))
     y, st = ops.conv3x3_fprop(a0, a1, wf, want_stats=True)
     dx0, dx1 = ops.conv3x3_dgrad(dy, wd, c0, c1)
+    # same dgrad with the column sums of dx0 taken in the epilogue (ConvTranspose bias gradient hand-off)
+    dx0b, dx1b, cs0 = ops.conv3x3_dgrad(dy, wd, c0, c1, want_colsum0=True)
     dw = ops.conv3x3_wgrad(a0, a1, dy)
     torch.cuda.synchronize()
     res = {'fprop': rel_err(nchw(y), yr.detach())}
+    res['dgrad_colsum0'] = rel_err(cs0, nchw(dx0).double().sum((0, 2, 3)))
+    assert torch.equal(dx0, dx0b) and (dx1 is None or torch.equal(dx1, dx1b)) and res['dgrad_colsum0'] < 1e-4, res
     s1, s2 = reduce_stats(st, cout)
     # the epilogue takes the statistics over the bf16 outputs it stores (the values BatchNorm then normalises)
     yk = nchw(y).double()
