@@ -750,6 +750,9 @@ CHECKS = {
     'conv3x3_pair_64_128': lambda: check_conv3x3(6, 128, 128, 64, 0, 128, seed=33),
     'conv3x3_pair_64_64': lambda: check_conv3x3(6, 128, 128, 64, 0, 64, seed=34),
     'conv3x3_pair_cat_64+64_64': lambda: check_conv3x3(5, 136, 120, 64, 64, 64, seed=35),
+    # single-patch staging (N = 64 tiles) on ragged shapes: W and H not multiples of the 8 x 16 tile, odd tile count
+    'conv3x3_pair_64_64_ragged': lambda: check_conv3x3(5, 100, 92, 64, 0, 64, seed=36),
+    'conv3x3_pair_128_64_ragged_odd': lambda: check_conv3x3(3, 140, 83, 128, 0, 64, seed=37),
     # BASELINE.json configs[1] full sizes (per-GPU batch 64 @512^2): first-level and bottleneck-level layers
     'conv3x3_full_size_enc1_conv2': lambda: check_conv3x3(64, 512, 512, 64, 0, 64, seed=50),
     'conv3x3_full_size_up4_conv1': lambda: check_conv3x3(64, 64, 64, 512, 512, 512, seed=51),
