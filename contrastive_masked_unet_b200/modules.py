@@ -178,16 +178,16 @@ class MaskStream:
 
 
 # --------------------------------------------------------------------------------------------------------- conv blocks
-def _bn_cfg(bn, pool, want_act=True, x0_colsum=False):
+def _bn_cfg(bn, pool, want_act=True):
     mom = bn.momentum if bn.momentum is not None else 0.1
-    return Fn.BNConfig(bn.training, mom, bn.eps, pool, want_act, x0_colsum)
+    return Fn.BNConfig(bn.training, mom, bn.eps, pool, want_act)
 
 
-def _conv_bn_relu(conv, bn, x0, x1=None, pool=False, want_act=True, x0_colsum=False):
+def _conv_bn_relu(conv, bn, x0, x1=None, pool=False, want_act=True):
     if bn.training and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     return Fn.ConvBNReLUFn.apply(Fn.to_act(x0), None if x1 is None else Fn.to_act(x1), conv.weight, conv.bias, bn.weight,
-                                 bn.bias, bn.running_mean, bn.running_var, _bn_cfg(bn, pool, want_act, x0_colsum))
+                                 bn.bias, bn.running_mean, bn.running_var, _bn_cfg(bn, pool, want_act))
 
 
 @register
@@ -203,7 +203,7 @@ class DoubleConv(nn.Module):
             nn.ReLU(inplace=True))
         self.in_channels, self.out_channels = in_channels, out_channels
 
-    def run(self, x, skip=None, mask=None, pool=False, want_skip=True, x_from_convT=False):
+    def run(self, x, skip=None, mask=None, pool=False, want_skip=True):
         """x: NCHW-shaped tensor (fp32 (N,1,H,W) for the first layer); skip: second concat source; mask: (B,H,W) uint8
         whose image 0 masks the whole batch (first layer only)."""
         seq = self.double_conv
@@ -218,7 +218,7 @@ class DoubleConv(nn.Module):
         else:
             if mask is not None:
                 raise CmuError('input masking is fused into the 1-channel first layer only')
-            a = _conv_bn_relu(seq[0], seq[1], x, skip, False, x0_colsum=x_from_convT)
+            a = _conv_bn_relu(seq[0], seq[1], x, skip, False)
         return _conv_bn_relu(seq[3], seq[4], a, None, pool, want_skip)
 
     def forward(self, x):
@@ -262,8 +262,7 @@ class UpBlock(nn.Module):
             raise NotImplementedError('bilinear up-sampling has no sm_100a kernel (and is shape-inconsistent in the '
                                       'reference: munet_neck.py:29-33)')
         up = Fn.ConvT2x2Fn.apply(Fn.to_act(down_input), self.up_sample.weight, self.up_sample.bias)
-        # the first conv's dgrad epilogue sums d(up) per channel on the way out: ConvTranspose bias gradient for free
-        return self.double_conv.run(up, skip=skip_input, x_from_convT=self.up_sample.bias is not None)
+        return self.double_conv.run(up, skip=skip_input)
 
 
 def _kaiming_init(module):
