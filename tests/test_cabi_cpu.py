@@ -20,7 +20,7 @@ GOLD = os.path.join(ROOT, 'tests', 'golden')
 
 def test_library_exports_every_declared_symbol():
     if not os.path.exists(LIB_PATH):
-        from contrastive_masked_unet_b200.build import build
+        from contrastive_masked_unet_b200._buildlib import build
         build()
     import ctypes
     dll = ctypes.CDLL(LIB_PATH)
@@ -246,3 +246,17 @@ def test_moco_queue_cache_signature_follows_buffer_writes():
     m.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})
     assert m._queue_sig() != s1
     assert m.shuffle_bn is True
+
+
+def test_model_factory_survives_importing_the_library_builder():
+    """`pkg.build(cfg)` (the stand-in for MODELS.build) keeps working after the driver's build() and after an explicit
+    import of the `build` submodule, which Python would otherwise bind over the factory."""
+    import importlib
+    import __graft_entry__ as G
+    G.build()
+    assert type(C.build(C.cmunet_config(64))).__name__ == 'CM_UNet'
+    importlib.import_module('contrastive_masked_unet_b200.build')
+    import contrastive_masked_unet_b200 as P
+    assert type(P.build(P.cmunet_config(64))).__name__ == 'CM_UNet'
+    from contrastive_masked_unet_b200.build import build as build_library
+    assert build_library.__module__.endswith('_buildlib')
