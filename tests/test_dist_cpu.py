@@ -53,6 +53,25 @@ def _worker(rank, world, port, out):
     yr = ref(torch.cat(xs, 0))[rank * 5:(rank + 1) * 5]
     res['syncbn_err'] = float((y - yr).abs().max())
     res['syncbn_rv_err'] = float((neck.bn0.running_var - ref.bn0.running_var).abs().max())
+    # (d) product host logic of MoCo's shuffle-BN (moco.py `_batch_shuffle_ddp` / `_batch_unshuffle_ddp` ==
+    # moco2_module.py:177-222): one permutation for all ranks, every sample visits exactly one rank, unshuffle restores
+    # each rank's own rows in order
+    import contrastive_masked_unet_b200 as C
+    torch.manual_seed(100 + rank)                      # different local seeds: the permutation must come from rank 0
+    m = C.Moco_v2(emb_dim=1024, num_negatives=64)
+    xb = torch.arange(6, dtype=torch.float32).reshape(6, 1) + 100.0 * rank          # rows tagged (rank, index)
+    shuffled, idx_unshuffle = m._batch_shuffle_ddp(xb)
+    gathered = [torch.empty_like(shuffled) for _ in range(world)]
+    dist.all_gather(gathered, shuffled)
+    union = torch.cat(gathered).flatten().sort().values
+    expect = torch.cat([torch.arange(6.) + 100.0 * r for r in range(world)])
+    res['shuffle_is_permutation'] = bool(torch.equal(union, expect))
+    res['shuffle_mixes_ranks'] = bool((shuffled.flatten() // 100 != rank).any())
+    restored = m._batch_unshuffle_ddp(shuffled * 2.0, idx_unshuffle)               # "encoder" = x -> 2x
+    res['unshuffle_ok'] = bool(torch.equal(restored, xb * 2.0))
+    idx_all = [torch.empty_like(idx_unshuffle) for _ in range(world)]
+    dist.all_gather(idx_all, idx_unshuffle)
+    res['same_permutation_on_all_ranks'] = bool(all(torch.equal(i, idx_all[0]) for i in idx_all))
     out[rank] = res
     dist.destroy_process_group()
 
@@ -68,4 +87,6 @@ def test_two_rank_head_semantics_gloo():
         assert o['d_proj_s_norm'] == pytest.approx(g['d_proj_s']['norm'], rel=1e-4)
         assert o['gather_ok'] and o['rank_world'] == (r, 2)
         assert o['syncbn_err'] < 1e-5 and o['syncbn_rv_err'] < 1e-5
+        assert o['shuffle_is_permutation'] and o['unshuffle_ok'] and o['same_permutation_on_all_ranks'], o
+    assert out[0]['shuffle_mixes_ranks'] or out[1]['shuffle_mixes_ranks']
     assert out[0]['loss_ct'] != out[1]['loss_ct']      # the label offset makes the ranks' losses differ
