@@ -35,7 +35,7 @@ def _nchw_view(a):
 
 
 class BNConfig:
-    __slots__ = ('training', 'momentum', 'eps', 'pool', 'grad', 'want_act')
+    __slots__ = ('training', 'momentum', 'eps', 'pool', 'grad', 'want_act', 'on_backward')
 
     def __init__(self, training, momentum, eps, pool, want_act=True):
         self.training, self.momentum, self.eps, self.pool = training, momentum, eps, pool
@@ -43,6 +43,7 @@ class BNConfig:
         # pooled layers whose full-resolution activation (the skip tensor) nobody reads: skip its store (backward
         # recomputes ReLU mask and pool routing from y, so the tensor is not needed for autograd either)
         self.want_act = want_act or not pool
+        self.on_backward = None                 # callable run once this node's backward kernels have been enqueued
 
 
 def _conv_bias_grad(dy, bn_training):
@@ -111,6 +112,7 @@ class FirstConvBNReLUFn(torch.autograd.Function):
         if cfg.grad and any(ctx.needs_input_grad):
             ctx.save_for_backward(x, mask, y, scale, shift, mean, rstd)
         ctx.bn_training = cfg.training
+        ctx.on_backward = cfg.on_backward
         return _nchw_view(act)
 
     @staticmethod
@@ -120,6 +122,8 @@ class FirstConvBNReLUFn(torch.autograd.Function):
         dy, dgamma, dbeta = ops.bn_relu_bwd(da, None, y, scale, shift, mean, rstd, ctx.bn_training)
         dw = ops.conv3x3_c1_wgrad(x, mask, dy) if ctx.needs_input_grad[2] else None
         dbias = _conv_bias_grad(dy, ctx.bn_training) if ctx.needs_input_grad[3] else None
+        if ctx.on_backward is not None:
+            ctx.on_backward()        # last node of the step's backward (e.g. the mask stream's deferred prefetch)
         # the input image never needs a gradient on this path (f1 "not needed")
         return None, None, dw, dbias, dgamma, dbeta, None, None, None
 

@@ -56,6 +56,9 @@ class MaskStream:
         self._target_owed = None     # (tkey, mid): online half consumed, its target half already drawn speculatively
         self._side = None
         self._last_key = None
+        self._deferred = None        # key of a pair to prefetch once the current step's backward has been enqueued
+        self.defer_prefetch = True   # fire the prefetch from the end of backward instead of right after the target call
+        self._grad_step = False      # the online call of this step ran with autograd on (a backward will follow)
 
     def _ensure(self, device):
         if self.state is None:
@@ -90,8 +93,18 @@ class MaskStream:
         w = st.cpu().numpy().view(np.uint32)
         return ('MT19937', w[:624].copy(), int(w[624]), 0, 0.0)
 
+    def fire_deferred_prefetch(self):
+        """Called when the step's backward has been enqueued (from the first layer's backward node): the single-warp
+        draw kernel then runs under the optimizer / EMA kernels instead of holding an SM while the persistent
+        tensor-core kernels of the forward pass want all 148 (same-box A/B: the early prefetch cost as much as it hid)."""
+        if self._deferred is not None and self._pref is None and self._target_owed is None:
+            key, dev = self._deferred
+            self._deferred = None
+            self._prefetch(key, dev)
+
     def _settle(self):
         """Roll the device state back to the logical stream position (undo whatever was drawn speculatively)."""
+        self._deferred = None
         if self._pref is not None:
             _, _, ev, backup, _ = self._pref
             torch.cuda.current_stream().wait_event(ev)
@@ -141,6 +154,8 @@ class MaskStream:
         if k > 0:                                             # online call
             key = (batch, img_size, patch_size, k)
             self._last_key = key
+            self._grad_step = torch.is_grad_enabled()
+            self._deferred = None
             if self._target_owed is not None:                 # previous online call was not followed by its target call
                 self._settle()
             if self._pref is not None and self._pref[0] == key:
@@ -163,7 +178,10 @@ class MaskStream:
             mask = self._launch(batch, img_size, patch_size, 0, batch, device)
         nxt = self._last_key
         if nxt is not None and nxt[:3] == tkey:
-            self._prefetch(nxt, device)                       # pair of the next step, on the side stream
+            if self.defer_prefetch and self._grad_step:
+                self._deferred = (nxt, device)                # fired by fire_deferred_prefetch() at the end of backward
+            else:
+                self._prefetch(nxt, device)                   # pair of the next step, on the side stream
         return mask, 0
 
     def __getstate__(self):
@@ -173,7 +191,7 @@ class MaskStream:
             d['state'] = d['_pref'][3]
         elif d.get('_target_owed') is not None:
             d['state'] = d['_target_owed'][1]
-        d['_pref'] = d['_side'] = d['_target_owed'] = None
+        d['_pref'] = d['_side'] = d['_target_owed'] = d['_deferred'] = None
         return d
 
 
@@ -203,7 +221,7 @@ class DoubleConv(nn.Module):
             nn.ReLU(inplace=True))
         self.in_channels, self.out_channels = in_channels, out_channels
 
-    def run(self, x, skip=None, mask=None, pool=False, want_skip=True):
+    def run(self, x, skip=None, mask=None, pool=False, want_skip=True, on_backward=None):
         """x: NCHW-shaped tensor (fp32 (N,1,H,W) for the first layer); skip: second concat source; mask: (B,H,W) uint8
         whose image 0 masks the whole batch (first layer only)."""
         seq = self.double_conv
@@ -212,9 +230,10 @@ class DoubleConv(nn.Module):
             bn = seq[1]
             if bn.training and bn.num_batches_tracked is not None:
                 bn.num_batches_tracked += 1
+            cfg = _bn_cfg(bn, False)
+            cfg.on_backward = on_backward
             a = Fn.FirstConvBNReLUFn.apply(x.reshape(x.shape[0], x.shape[-2], x.shape[-1]), mask, seq[0].weight,
-                                           seq[0].bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                           _bn_cfg(bn, False))
+                                           seq[0].bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, cfg)
         else:
             if mask is not None:
                 raise CmuError('input masking is fused into the 1-channel first layer only')
@@ -234,10 +253,10 @@ class DownBlock(nn.Module):
         self.double_conv = DoubleConv(in_channels, out_channels)
         self.down_sample = nn.MaxPool2d(2)
 
-    def forward(self, x, mask=None, want_skip=True):
+    def forward(self, x, mask=None, want_skip=True, on_backward=None):
         """want_skip=False: the full-resolution skip tensor is not written and comes back as None (the frozen target
         encoder of CM_UNet and the MoCo encoders only use the pooled path; backward does not need the tensor)."""
-        skip_out, down_out = self.double_conv.run(x, mask=mask, pool=True, want_skip=want_skip)
+        skip_out, down_out = self.double_conv.run(x, mask=mask, pool=True, want_skip=want_skip, on_backward=on_backward)
         return (down_out, skip_out)
 
 
@@ -304,7 +323,8 @@ class UNet_encoder(nn.Module):
         b, s = x.shape[0], x.shape[1]
         mask, k = self.mask_stream.generate(b, s, self.patch_size, self.mask_ratio, x.device)
         x = x.unsqueeze(1)
-        x, skip1_out = self.down_conv1(x, mask=mask if k > 0 else None, want_skip=want_skips)   # fused x * (1 - mask[0])  (:156, Q1)
+        x, skip1_out = self.down_conv1(x, mask=mask if k > 0 else None, want_skip=want_skips,     # fused x * (1 - mask[0])  (:156, Q1)
+                                       on_backward=self.mask_stream.fire_deferred_prefetch if k > 0 else None)
         x, skip2_out = self.down_conv2(x, want_skip=want_skips)
         x, skip3_out = self.down_conv3(x, want_skip=want_skips)
         x, skip4_out = self.down_conv4(x, want_skip=want_skips)

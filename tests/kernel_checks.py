@@ -369,9 +369,12 @@ def check_mask_pair_mode(seed=60, b=5, s=96, steps=4):
     dev = torch.device(DEV)
     bad = 0
     batches = [b, b, b, b + 2, b + 2, b]
-    for bb in batches[:steps + 2]:
+    for step_i, bb in enumerate(batches[:steps + 2]):
         m_on, k = ms.generate(bb, s, 16, 0.65, dev)
         m_tg, k0 = ms.generate(bb, s, 16, 0.0, dev)
+        if step_i != 1:
+            ms.fire_deferred_prefetch()        # what the first layer's backward node does at the end of a training step
+        # (step 1: no backward ran -> the deferred prefetch is dropped and the next pair is generated synchronously)
         ref, _ = patch_mask(rng, bb, s, 16, 0.65)
         patch_mask(rng, bb, s, 16, 0.0)
         torch.cuda.synchronize()
@@ -381,7 +384,7 @@ def check_mask_pair_mode(seed=60, b=5, s=96, steps=4):
     r2.set_state(st[1], st[2])
     ok = [r2.next_u32() for _ in range(3)] == [rng.next_u32() for _ in range(3)]
     res = {'mismatch_bytes': bad, 'logical_stream_ok': ok, 'prefetch_outstanding': ms._pref is not None}
-    assert bad == 0 and ok, res
+    assert bad == 0 and ok and res['prefetch_outstanding'], res
     return res
 
 
@@ -410,6 +413,7 @@ def check_mask_interleaved_calls(seed=62, b=4, s=96):
     def target(bb, ss):
         nonlocal bad
         m, _ = ms.generate(bb, ss, 16, 0.0, dev)
+        ms.fire_deferred_prefetch()        # end of the training step's backward
         patch_mask(rng, bb, ss, 16, 0.0)
         bad += int(m.sum())
 
