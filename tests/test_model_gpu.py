@@ -214,3 +214,42 @@ def test_moco_resume_from_state_dict_uses_loaded_queue_and_pointer():
     assert float((m._rows.float() - m.queue.t()).abs().max()) < 1e-2
     # without the cache invalidation the stale rows / pointer would have been used: the step-2 keys sit in columns 64..127
     assert not torch.equal(saved['queue'][:, 64:128], m.queue[:, 64:128])
+
+
+def test_mask_stream_position_after_training_steps_with_deferred_prefetch():
+    """three fwd+bwd steps (the prefetch of the next pair is fired from the backward thread), then the stream position
+    and the next online mask equal numpy's after 3 x (B online + B target) shuffles -- bit-exact (Q2)."""
+    _gpu()
+    import numpy as np
+    import contrastive_masked_unet_b200 as C
+    from oracle.mask_oracle import MT19937, patch_mask
+    S, B, seed = 64, 6, 77
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    m = C.build(C.cmunet_config(S))
+    m.init_weights()
+    m = m.cuda().train()
+    rng = MT19937(seed)
+    g = torch.Generator().manual_seed(1)
+    for step in range(3):
+        img = torch.randn(B, S, S, generator=g).cuda()
+        out = m(img, mode='loss', img_t=img + 0.1)
+        (out['loss_ct'] + out['loss_rc']).backward()
+        patch_mask(rng, B, S, 16, 0.65)
+        patch_mask(rng, B, S, 16, 0.0)
+        assert m.backbone.mask_stream._pref is not None, 'the deferred prefetch must have fired at the end of backward'
+    torch.cuda.synchronize()
+    st = m.backbone.mask_stream.get_numpy_state()
+    r2 = MT19937()
+    r2.set_state(st[1], st[2])
+    key, pos = rng.get_state()
+    r3 = MT19937()
+    r3.set_state(key, pos)
+    assert [r2.next_u32() for _ in range(4)] == [r3.next_u32() for _ in range(4)]
+    _, mask, _ = m(torch.randn(B, S, S, generator=g).cuda(), mode='tensor')      # consumes the prefetched online half
+    ref, _ = patch_mask(rng, B, S, 16, 0.65)
+    assert np.array_equal(mask.cpu().numpy(), ref)
+    # no target call followed: the speculatively drawn target half is rolled back for the next call
+    _, mask2, _ = m(torch.randn(B, S, S, generator=g).cuda(), mode='tensor')
+    ref2, _ = patch_mask(rng, B, S, 16, 0.65)
+    assert np.array_equal(mask2.cpu().numpy(), ref2)
