@@ -45,7 +45,7 @@ def parse_header(path=HEADER_PATH):
 
 
 # int-returning functions whose result is a value, not a status code
-VALUE_FUNCS = {'cmu_version', 'cmu_mask_state_words', 'cmu_mask_workspace_bytes', 'cmu_conv3x3_c1_grid', 'cmu_conv_max_grid', 'cmu_bn_bwd_grid'}
+VALUE_FUNCS = {'cmu_version', 'cmu_mask_state_words', 'cmu_mask_workspace_bytes', 'cmu_conv3x3_c1_grid', 'cmu_conv_max_grid', 'cmu_bn_bwd_grid', 'cmu_bn_relu_head_grid'}
 
 
 class CmuError(RuntimeError):

@@ -2,6 +2,7 @@
 Finetuning/metrics.py (:19-82 Loss algebra and `__name__`s, :135-220 Dice / IoU, :503-504 CrossEntropyLoss).
 Dice / IoU / CE of one (pred, gt) pair come from ONE fused reduction kernel (cached per input pair), CE's gradient
 from the same launch.  Quirk Q7 is kept: the thresholded Dice / IoU terms carry no gradient; results are float64."""
+import os
 import re
 
 import torch
@@ -10,7 +11,7 @@ import torch.nn as nn
 from . import functional as Fn
 from . import ops
 from ._lib import lib
-from .modules import DoubleConv, DownBlock, UpBlock, register  # noqa: F401
+from .modules import DoubleConv, DownBlock, UpBlock, _head_fusable, register  # noqa: F401
 
 
 @register
@@ -45,6 +46,8 @@ class UNet(nn.Module):
         x = self.up_conv4(x, skip4_out)
         x = self.up_conv3(x, skip3_out)
         x = self.up_conv2(x, skip2_out)
+        if _head_fusable(self.conv_last) and os.environ.get('CMU_NO_HEAD_FUSION') != '1':
+            return self.up_conv1(x, skip1_out, head=self.conv_last)      # BN + ReLU folded into conv_last (head_fused.cu)
         x = self.up_conv1(x, skip1_out)
         return Fn.Head1x1Fn.apply(Fn.to_act(x), self.conv_last.weight, self.conv_last.bias)
 

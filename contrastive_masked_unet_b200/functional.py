@@ -98,6 +98,43 @@ class ConvBNReLUFn(torch.autograd.Function):
         return dx0, dx1, dw, dbias, dgamma, dbeta, None, None, None
 
 
+class ConvBNReLUHeadFn(torch.autograd.Function):
+    """Conv3x3(pad 1) -> BatchNorm2d -> ReLU -> Conv2d(64, 2, 1): the last DoubleConv layer of a decoder fused with
+    `conv_last` (munet_neck.py:48-49,72,81 == FT/model.py:79-81,131).  The activated 64-channel tensor and its gradient
+    never reach HBM: BN apply + ReLU run in the prologue of the 1x1 head (forward) and of the BatchNorm backward passes,
+    which rebuild da = W_head^T dout on the fly (csrc/head_fused.cu).  -> (N,2,H,W) fp32."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, weight, bias, gamma, beta, running_mean, running_var, head_w, head_b, cfg):
+        a0 = _nhwc(x0)
+        a1 = _nhwc(x1) if x1 is not None else None
+        need_grad = cfg.grad and any(ctx.needs_input_grad)
+        wf, wd = ops.pack_conv3x3(weight, need_dgrad=need_grad)
+        y, stats = ops.conv3x3_fprop(a0, a1, wf, want_stats=cfg.training)
+        scale, shift, mean, rstd = ops.bn_finalize(stats, gamma, beta, bias, running_mean, running_var, cfg.momentum,
+                                                   cfg.eps, cfg.training)
+        out = ops.bn_relu_head_fwd(y, scale, shift, head_w, head_b)
+        if need_grad:
+            ctx.save_for_backward(a0, a1, y, scale, shift, mean, rstd, wd, head_w)
+            ctx.c0 = a0.shape[3]
+            ctx.c1 = 0 if a1 is None else a1.shape[3]
+        ctx.bn_training = cfg.training
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        a0, a1, y, scale, shift, mean, rstd, wd, head_w = ctx.saved_tensors
+        dy, dgamma, dbeta, dhw, dhb = ops.bn_relu_head_bwd(y, scale, shift, mean, rstd, head_w, d_out, ctx.bn_training)
+        dx0 = dx1 = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            g0, g1 = ops.conv3x3_dgrad(dy, wd, ctx.c0, ctx.c1)
+            dx0 = _nchw_view(g0) if ctx.needs_input_grad[0] else None
+            dx1 = _nchw_view(g1) if (g1 is not None and ctx.needs_input_grad[1]) else None
+        dw = ops.conv3x3_wgrad(a0, a1, dy) if ctx.needs_input_grad[2] else None
+        dbias = _conv_bias_grad(dy, ctx.bn_training) if ctx.needs_input_grad[3] else None
+        return (dx0, dx1, dw, dbias, dgamma, dbeta, None, None, dhw.reshape(head_w.shape).clone(), dhb.clone(), None)
+
+
 class FirstConvBNReLUFn(torch.autograd.Function):
     """Cin = 1 first layer: (x * (1 - mask[0])) -> Conv3x3 -> BN -> ReLU.  x: (N,H,W) fp32; mask: (B,H,W) uint8 or
     None (UNet_encoder.py:77,156; quirk Q1)."""

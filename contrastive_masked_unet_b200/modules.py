@@ -7,6 +7,7 @@ The `nn.Conv2d` / `nn.BatchNorm2d` / `nn.Linear` children exist only as PARAMETE
 reference's key names, default initialisation and RNG consumption); their own forward is never called.
 CUDA (sm_100a) only: CPU tensors raise, there is no fallback."""
 import math
+import os
 
 import numpy as np
 import torch
@@ -208,6 +209,19 @@ def _conv_bn_relu(conv, bn, x0, x1=None, pool=False, want_act=True):
                                  bn.bias, bn.running_mean, bn.running_var, _bn_cfg(bn, pool, want_act))
 
 
+def _head_fusable(head):
+    """conv_last shapes the fused decoder tail is written for (64 -> 2, 1x1): the only ones the reference configs use."""
+    return (isinstance(head, nn.Conv2d) and head.in_channels == 64 and head.out_channels == 2 and
+            head.kernel_size == (1, 1) and head.bias is not None)
+
+
+def _conv_bn_relu_head(conv, bn, head, x0):
+    if bn.training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return Fn.ConvBNReLUHeadFn.apply(Fn.to_act(x0), None, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean,
+                                     bn.running_var, head.weight, head.bias, _bn_cfg(bn, False))
+
+
 @register
 class DoubleConv(nn.Module):
     """[Conv3x3 -> BatchNorm2d -> ReLU] x 2 (UNet_encoder.py:8-30)."""
@@ -221,7 +235,7 @@ class DoubleConv(nn.Module):
             nn.ReLU(inplace=True))
         self.in_channels, self.out_channels = in_channels, out_channels
 
-    def run(self, x, skip=None, mask=None, pool=False, want_skip=True, on_backward=None):
+    def run(self, x, skip=None, mask=None, pool=False, want_skip=True, on_backward=None, head=None):
         """x: NCHW-shaped tensor (fp32 (N,1,H,W) for the first layer); skip: second concat source; mask: (B,H,W) uint8
         whose image 0 masks the whole batch (first layer only)."""
         seq = self.double_conv
@@ -238,6 +252,8 @@ class DoubleConv(nn.Module):
             if mask is not None:
                 raise CmuError('input masking is fused into the 1-channel first layer only')
             a = _conv_bn_relu(seq[0], seq[1], x, skip, False)
+        if head is not None:      # decoder tail: second conv + BN + ReLU + conv_last in one autograd node (no `a` in HBM)
+            return _conv_bn_relu_head(seq[3], seq[4], head, a)
         return _conv_bn_relu(seq[3], seq[4], a, None, pool, want_skip)
 
     def forward(self, x):
@@ -276,12 +292,14 @@ class UpBlock(nn.Module):
         self.up_sample_mode = up_sample_mode
         self.double_conv = DoubleConv(in_channels, out_channels)
 
-    def forward(self, down_input, skip_input):
+    def forward(self, down_input, skip_input, head=None):
+        """head: the decoder's `conv_last` (64 -> 2) to fuse behind the block -- then the block returns the head's output
+        (N,2,H,W) fp32 instead of its own activation (which is never materialised)."""
         if self.up_sample_mode != 'conv_transpose':
             raise NotImplementedError('bilinear up-sampling has no sm_100a kernel (and is shape-inconsistent in the '
                                       'reference: munet_neck.py:29-33)')
         up = Fn.ConvT2x2Fn.apply(Fn.to_act(down_input), self.up_sample.weight, self.up_sample.bias)
-        return self.double_conv.run(up, skip=skip_input)
+        return self.double_conv.run(up, skip=skip_input, head=head)
 
 
 def _kaiming_init(module):
@@ -364,6 +382,8 @@ class MUNetPretrainDecoder(nn.Module):
         x = self.up_conv4(x, skip[3])
         x = self.up_conv3(x, skip[2])
         x = self.up_conv2(x, skip[1])
+        if _head_fusable(self.conv_last) and os.environ.get('CMU_NO_HEAD_FUSION') != '1':     # A/B switch
+            return self.up_conv1(x, skip[0], head=self.conv_last)
         x = self.up_conv1(x, skip[0])
         return Fn.Head1x1Fn.apply(Fn.to_act(x), self.conv_last.weight, self.conv_last.bias)
 

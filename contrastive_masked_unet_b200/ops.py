@@ -338,6 +338,31 @@ def head1x1_bwd(a, w, dout):
     return da, acc[:128].view(2, 64), acc[128:130]
 
 
+def bn_relu_head_fwd(y, scale, shift, w, b):
+    """conv_last(relu(y * scale + shift)) for a 64-channel raw conv output y (act) -> (N,2,H,W) fp32; the activated
+    tensor is never written."""
+    n, h, wd, cin = _act(y).shape
+    w2 = w.detach().reshape(w.shape[0], -1).contiguous().float()
+    out = torch.empty(n, w2.shape[0], h, wd, dtype=torch.float32, device=y.device)
+    lib.cmu_bn_relu_head_fwd(_ptr(y), _ptr(scale), _ptr(shift), _ptr(w2), _ptr(b.detach().contiguous().float()), _ptr(out),
+                             n, h, wd, cin, w2.shape[0], _stream())
+    return out
+
+
+def bn_relu_head_bwd(y, scale, shift, mean, rstd, w, dout, training=True):
+    """-> (dy act, dgamma (64,), dbeta (64,), d conv_last.weight (2,64), d conv_last.bias (2,))."""
+    n, h, wd, cin = _act(y).shape
+    w2 = w.detach().reshape(w.shape[0], -1).contiguous().float()
+    dout = dout.contiguous().float()
+    partial = torch.empty(lib.cmu_bn_relu_head_grid() * 258, dtype=torch.float32, device=y.device)
+    sums = torch.empty(2, cin, dtype=torch.float32, device=y.device)
+    acc = torch.empty(130, dtype=torch.float32, device=y.device)
+    dy = torch.empty_like(y)
+    lib.cmu_bn_relu_head_bwd(_ptr(y), _ptr(scale), _ptr(shift), _ptr(mean), _ptr(rstd), _ptr(w2), _ptr(dout), _ptr(partial),
+                             _ptr(sums), _ptr(acc), _ptr(dy), n, h, wd, cin, w2.shape[0], int(training), _stream())
+    return dy, sums[1], sums[0], acc[:128].view(2, 64), acc[128:130]
+
+
 # ------------------------------------------------------------------------------------------- linear / BN1d
 def sgemm(a, sam, sak, b, sbn, sbk, m, n, k, bias=None, out=None, accumulate=False):
     dev = a.device

@@ -119,6 +119,17 @@ int cmu_head1x1_fprop(const void* a, const float* w, const float* b, float* out 
                       int cin, int cout, void* stream);
 int cmu_head1x1_bwd(const void* a, const float* w, const float* dout, void* da, float* acc /* float[130] */, int n, int h,
                     int w_, int cin, int cout, void* stream);
+/* decoder tail fused (munet_neck.py:48-49,72,81 == FT/model.py:79-81,131): BatchNorm apply + ReLU of the last 64-channel
+ * conv folded into conv_last, forward and backward; the activated tensor `a` and its gradient never reach HBM.
+ * y: raw conv output (act, 64 ch); scale/shift/mean/rstd from cmu_bn_finalize; w (2,64), b (2) = conv_last parameters.
+ * bwd: partial = float[cmu_bn_relu_head_grid()][258] scratch; sums[2][64] = (dbeta, dgamma) of that BatchNorm;
+ * acc[130] = d conv_last.weight (2,64) followed by d conv_last.bias (2); dy = gradient of y (act). */
+int cmu_bn_relu_head_grid(void);
+int cmu_bn_relu_head_fwd(const void* y, const float* scale, const float* shift, const float* w, const float* b, float* out,
+                         int n, int h, int wd, int cin, int cout, void* stream);
+int cmu_bn_relu_head_bwd(const void* y, const float* scale, const float* shift, const float* mean, const float* rstd,
+                         const float* w, const float* dout, float* partial, float* sums, float* acc, void* dy, int n, int h,
+                         int wd, int cin, int cout, int training, void* stream);
 
 /* ---- a7  NonLinearNeck: CMU/necks/nonlinear_neck.py:88-103 ------------------------------------------------ */
 long long cmu_sgemm_workspace_bytes(int m, int n, int k);

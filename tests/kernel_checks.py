@@ -267,6 +267,54 @@ def check_bn(n=3, h=16, w=24, c=64, pool=True, seed=5):
     return res
 
 
+def check_bn_relu_head(n=3, h=20, w=28, seed=21, training=True):
+    """fused decoder tail (BN apply + ReLU folded into conv_last, forward and backward) vs the unfused kernels of this
+    library (bit-compatible up to summation order) and vs an fp32 torch statement."""
+    c = 64
+    g = _gen(seed)
+    yv = _randn((n, c, h, w), g, 1.5) + 0.3
+    gamma = (torch.rand(c, generator=g) + 0.5).to(DEV)
+    beta = _randn((c,), g, 0.3)
+    hw_ = _randn((2, c, 1, 1), g, 0.2)
+    hb = _randn((2,), g, 0.1)
+    dout = _randn((n, 2, h, w), g)
+    y = nhwc(yv)
+    yf = nchw(y)
+    st = ops.ConvStats(torch.cat([yf.sum((0, 2, 3)), (yf ** 2).sum((0, 2, 3))]).float().contiguous(), 1, c, float(n * h * w))
+    rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    scale, shift, mean, rstd = ops.bn_finalize(st, gamma, beta, None, rm, rv, 0.1, 1e-5, True)
+    if not training:
+        scale, shift, mean, rstd = ops.bn_finalize(None, gamma, beta, None, rm, rv, 0.1, 1e-5, False)
+    # fused
+    out = ops.bn_relu_head_fwd(y, scale, shift, hw_, hb)
+    dy, dgamma, dbeta, dhw, dhb = ops.bn_relu_head_bwd(y, scale, shift, mean, rstd, hw_, dout, training)
+    # unfused kernels of the library
+    a, _ = ops.bn_relu_apply(y, scale, shift, False)
+    out_u = ops.head1x1_fprop(a, hw_, hb)
+    da_u, dhw_u, dhb_u = ops.head1x1_bwd(a, hw_, dout)
+    dy_u, dgamma_u, dbeta_u = ops.bn_relu_bwd(da_u, None, y, scale, shift, mean, rstd, training)
+    # fp32 torch statement on the same bf16 y
+    yin = yf.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    hwr, hbr = hw_.clone().requires_grad_(True), hb.clone().requires_grad_(True)
+    if training:
+        ar = F.relu(F.batch_norm(yin, None, None, gr, br, True, 0.1, 1e-5))
+    else:
+        ar = F.relu(F.batch_norm(yin, rm.clone(), rv.clone(), gr, br, False, 0.1, 1e-5))
+    pr = F.conv2d(ar, hwr, hbr)
+    (pr * dout).sum().backward()
+    torch.cuda.synchronize()
+    res = {'fwd_vs_unfused': rel_err(out, out_u), 'dy_vs_unfused': rel_err(nchw(dy), nchw(dy_u)),
+           'dgamma_vs_unfused': rel_err(dgamma, dgamma_u), 'dbeta_vs_unfused': rel_err(dbeta, dbeta_u),
+           'dhw_vs_unfused': rel_err(dhw, dhw_u), 'dhb_vs_unfused': rel_err(dhb, dhb_u),
+           'fwd': rel_err(out, pr.detach()), 'dy': rel_err(nchw(dy), yin.grad), 'dgamma': rel_err(dgamma, gr.grad),
+           'dbeta': rel_err(dbeta, br.grad), 'dhw': rel_err(dhw.reshape(2, c), hwr.grad.reshape(2, c)), 'dhb': rel_err(dhb, hbr.grad)}
+    assert max(res[k] for k in res if k.endswith('_vs_unfused')) < 2e-5, res
+    assert res['fwd'] < 1e-2 and res['dy'] < 2e-2 and res['dgamma'] < 5e-3 and res['dbeta'] < 5e-3, res
+    assert res['dhw'] < 5e-3 and res['dhb'] < 1e-5, res
+    return res
+
+
 # ------------------------------------------------------------------------------------------------ head losses
 def check_masked_mse(b=5, s=48, seed=6):
     from oracle import cmunet_oracle as O
@@ -774,6 +822,9 @@ CHECKS = {
     'convT_256_128_ragged': lambda: check_convT(2, 14, 14, 256, 128, seed=13),
     'conv1x1_1024_256': check_conv1x1,
     'head1x1': check_head1x1,
+    'bn_relu_head_fused': check_bn_relu_head,
+    'bn_relu_head_fused_ragged': lambda: check_bn_relu_head(2, 13, 37, seed=22),
+    'bn_relu_head_fused_eval': lambda: check_bn_relu_head(2, 16, 16, seed=23, training=False),
     'bn_pool': lambda: check_bn(3, 16, 24, 64, True),
     'bn_nopool_c256': lambda: check_bn(2, 10, 6, 256, False, seed=15),
     'bn_pool_c1024': lambda: check_bn(2, 4, 4, 1024, True, seed=16),
