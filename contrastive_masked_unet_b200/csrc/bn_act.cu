@@ -253,20 +253,9 @@ __global__ void __launch_bounds__(256) conv_c1_fprop_kernel(const float* __restr
 }
 
 // dW[co][r][s] = sum_p dy[p,co] * xm[p + (r-1, s-1)]; partial[block][64*9], reduced by a second tiny kernel.
-// kFusedBN: `dy` is the incoming gradient dA of the ACTIVATED first-layer output and the BatchNorm + ReLU backward is
-// applied on the fly from the raw conv output y (dy = scale * (dz - sum_dz/n - xhat * sum_dzx/n), rounded to bf16 like the
-// stand-alone apply pass stores it): the first layer needs no dgrad, so its dy has no other consumer and never
-// reaches HBM (saves one write and one read of the 64-channel full-resolution tensor).
-struct C1BnArgs {
-  const __nv_bfloat16* y;
-  const float *scale, *shift, *mean, *rstd, *sums;
-  float inv_count;
-};
-
-template <bool kFusedBN>
 __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restrict__ x, const uint8_t* __restrict__ mask0,
                                                             const __nv_bfloat16* __restrict__ dy, float* __restrict__ partial,
-                                                            int N, int H, int W, C1BnArgs bn) {
+                                                            int N, int H, int W) {
   extern __shared__ float c1_smem[];
   float* srow = c1_smem;
   const int pitch = W + 2;
@@ -274,19 +263,6 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restr
   for (int i = threadIdx.x; i < kC1Cout * 9; i += blockDim.x) sred[i] = 0.f;
   const int cg = threadIdx.x & 7;
   const int px = threadIdx.x >> 3;
-  float sc[8], sh[8], mu[8], rs[8], k1[8], k2[8];
-  if (kFusedBN) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = cg * 8 + k;
-      sc[k] = bn.scale[c];
-      sh[k] = bn.shift[c];
-      mu[k] = bn.mean[c];
-      rs[k] = bn.rstd[c];
-      k1[k] = bn.sums[c] * bn.inv_count;
-      k2[k] = bn.sums[kC1Cout + c] * bn.inv_count;
-    }
-  }
   float2 acc2[4][9];   // channel pairs: packed fp32 FMA (FFMA2), bit-identical to the scalar accumulation
 #pragma unroll
   for (int c = 0; c < 4; ++c)
@@ -301,7 +277,6 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restr
     __syncthreads();
     for (int rr = 0; rr < kC1Rows && h0 + rr < H; ++rr) {
       const uint4* grow = reinterpret_cast<const uint4*>(dy) + ((size_t)nb * H + h0 + rr) * W * 8;
-      const uint4* yrow = kFusedBN ? reinterpret_cast<const uint4*>(bn.y) + ((size_t)nb * H + h0 + rr) * W * 8 : nullptr;
       const float* sr = srow + rr * pitch;
       for (int w0 = 0; w0 < W; w0 += 32) {
         const int wq = w0 + px;
@@ -316,17 +291,6 @@ __global__ void __launch_bounds__(256) conv_c1_wgrad_kernel(const float* __restr
             }
           float g[8];
           unpack8(__ldcs(grow + wq * 8 + cg), g);
-          if (kFusedBN) {
-            float yv[8];
-            unpack8(__ldcs(yrow + wq * 8 + cg), yv);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float z = fmaf(yv[k], sc[k], sh[k]);
-              const float dz = (z > 0.f) ? g[k] : 0.f;
-              const float xh = (yv[k] - mu[k]) * rs[k];
-              g[k] = __bfloat162float(__float2bfloat16_rn(sc[k] * (dz - k1[k] - xh * k2[k])));
-            }
-          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float2 gp = make_float2(g[2 * c], g[2 * c + 1]);
@@ -817,46 +781,14 @@ int cmu_conv3x3_c1_wgrad(const float* x, const unsigned char* mask0, const void*
   const int c1_shmem = (kC1Rows + 2) * (wd + 2) * (int)sizeof(float);
   static bool attr_w = false;
   if (!attr_w) {
-    CMU_CHECK_CUDA(cudaFuncSetAttribute(conv_c1_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CMU_CHECK_CUDA(cudaFuncSetAttribute(conv_c1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (kC1Rows + 2) * (kC1MaxW + 2) * (int)sizeof(float)));
     attr_w = true;
   }
-  conv_c1_wgrad_kernel<false><<<grid, 256, c1_shmem, (cudaStream_t)stream>>>(x, mask0, (const __nv_bfloat16*)dy, partial, n, h,
-                                                                             wd, C1BnArgs{});
+  conv_c1_wgrad_kernel<<<grid, 256, c1_shmem, (cudaStream_t)stream>>>(x, mask0, (const __nv_bfloat16*)dy, partial, n, h, wd);
   CMU_LAUNCH_CHECK();
   reduce_rows_kernel<<<ceil_div(kC1Cout * 9, 32), 256, 0, (cudaStream_t)stream>>>(partial, dw, grid, kC1Cout * 9,
                                                                                    accumulate);
-  CMU_LAUNCH_CHECK();
-  return 0;
-}
-
-// First-layer backward with the BatchNorm + ReLU backward folded in: da = gradient of the ACTIVATED output, y = raw conv
-// output; sums[2][64] receives (sum dz, sum dz*xhat) = (dbeta, dgamma); dy is never written (the 1-channel input needs no
-// gradient, so wgrad is dy's only consumer).  bn_partial: float[cmu_bn_bwd_grid()][128], wg_partial: float[grid][576].
-int cmu_conv3x3_c1_bn_wgrad(const float* x, const unsigned char* mask0, const void* da, const void* y, const float* scale,
-                            const float* shift, const float* mean, const float* rstd, float* bn_partial, float* sums,
-                            float* wg_partial, float* dw, int n, int h, int wd, int training, void* stream) {
-  CMU_REQUIRE(wd <= kC1MaxW, "conv3x3_c1: image width %d exceeds %d", wd, kC1MaxW);
-  // pass 1: the statistics of the BatchNorm backward (reduce only)
-  if (cmu_bn_relu_bwd(da, nullptr, y, scale, shift, mean, rstd, bn_partial, sums, nullptr, n, h, wd, kC1Cout, training,
-                      stream))
-    return 1;
-  const int grid = cmu_conv3x3_c1_grid();
-  const int c1_shmem = (kC1Rows + 2) * (wd + 2) * (int)sizeof(float);
-  static bool attr_wf = false;
-  if (!attr_wf) {
-    CMU_CHECK_CUDA(cudaFuncSetAttribute(conv_c1_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (kC1Rows + 2) * (kC1MaxW + 2) * (int)sizeof(float)));
-    attr_wf = true;
-  }
-  C1BnArgs bn;
-  bn.y = (const __nv_bfloat16*)y;
-  bn.scale = scale; bn.shift = shift; bn.mean = mean; bn.rstd = rstd; bn.sums = sums;
-  bn.inv_count = training ? 1.f / ((float)n * h * wd) : 0.f;
-  conv_c1_wgrad_kernel<true><<<grid, 256, c1_shmem, (cudaStream_t)stream>>>(x, mask0, (const __nv_bfloat16*)da, wg_partial, n,
-                                                                            h, wd, bn);
-  CMU_LAUNCH_CHECK();
-  reduce_rows_kernel<<<ceil_div(kC1Cout * 9, 32), 256, 0, (cudaStream_t)stream>>>(wg_partial, dw, grid, kC1Cout * 9, 0);
   CMU_LAUNCH_CHECK();
   return 0;
 }
@@ -943,7 +875,6 @@ int cmu_bn_relu_bwd(const void* da, const void* dpool, const void* y, const floa
     reduce_rows_kernel<<<ceil_div(2 * c, 32), 256, 0, st>>>(partial, sums, g, 2 * c, 0);
   }
   CMU_LAUNCH_CHECK();
-  if (dy == nullptr) return 0;   // reduce only: the caller folds the apply pass into its own kernel (first-layer wgrad)
   if (dpool != nullptr)
     bn_bwd_kernel<true, true><<<sms * resident_blocks(bn_bwd_kernel<true, true>, 256, 6 * (size_t)c * sizeof(float)), 256,
                                 6 * (size_t)c * sizeof(float), st>>>(

@@ -4,8 +4,6 @@ Public tensors keep the reference's NCHW *shape*; activations travel as bf16 ten
 (channels-last strides), so `t.permute(0, 2, 3, 1)` is the contiguous (N,H,W,C) buffer the kernels use and nothing
 is ever transposed between layers.  Backward of train-mode BatchNorm follows SURVEY.md Appendix C; the conv bias in
 front of a train-mode BN has an analytically zero gradient (returned as zeros)."""
-import os
-
 import torch
 import torch.distributed as dist
 
@@ -13,7 +11,6 @@ from . import ops
 from ._lib import CmuError
 
 BF16 = torch.bfloat16
-FUSE_C1_BN_WGRAD = os.environ.get('CMU_NO_C1_FUSION') != '1'      # A/B switch (first-layer backward fusion)
 
 
 def to_act(x):
@@ -159,15 +156,9 @@ class FirstConvBNReLUFn(torch.autograd.Function):
     def backward(ctx, d_act):
         x, mask, y, scale, shift, mean, rstd = ctx.saved_tensors
         da = _nhwc(to_act(d_act))
-        if ctx.bn_training and ctx.needs_input_grad[2] and FUSE_C1_BN_WGRAD:
-            # BatchNorm + ReLU backward folded into the weight-gradient kernel: dy has no other consumer (no dgrad for
-            # the 1-channel input) and is never written
-            dw, dgamma, dbeta = ops.conv3x3_c1_bn_wgrad(x, mask, da, y, scale, shift, mean, rstd, True)
-            dbias = torch.zeros(da.shape[3], dtype=torch.float32, device=da.device) if ctx.needs_input_grad[3] else None
-        else:
-            dy, dgamma, dbeta = ops.bn_relu_bwd(da, None, y, scale, shift, mean, rstd, ctx.bn_training)
-            dw = ops.conv3x3_c1_wgrad(x, mask, dy) if ctx.needs_input_grad[2] else None
-            dbias = _conv_bias_grad(dy, ctx.bn_training) if ctx.needs_input_grad[3] else None
+        dy, dgamma, dbeta = ops.bn_relu_bwd(da, None, y, scale, shift, mean, rstd, ctx.bn_training)
+        dw = ops.conv3x3_c1_wgrad(x, mask, dy) if ctx.needs_input_grad[2] else None
+        dbias = _conv_bias_grad(dy, ctx.bn_training) if ctx.needs_input_grad[3] else None
         if ctx.on_backward is not None:
             ctx.on_backward()        # last node of the step's backward (e.g. the mask stream's deferred prefetch)
         # the input image never needs a gradient on this path (f1 "not needed")

@@ -216,23 +216,6 @@ def conv3x3_c1_wgrad(x, mask0, dy):
     return dw
 
 
-def conv3x3_c1_bn_wgrad(x, mask0, da, y, scale, shift, mean, rstd, training=True):
-    """First layer: BatchNorm + ReLU backward folded into the Cin = 1 weight gradient (dy never written).
-    -> (dw (64,1,3,3), dgamma (64,), dbeta (64,))."""
-    _need_cuda(x, da)
-    x = x.contiguous().float()
-    n, h, wd = x.shape
-    cout = _act(da).shape[3]
-    bn_partial = torch.empty(lib.cmu_bn_bwd_grid() * 2 * cout, dtype=torch.float32, device=x.device)
-    sums = torch.empty(2, cout, dtype=torch.float32, device=x.device)
-    wg_partial = torch.empty(lib.cmu_conv3x3_c1_grid() * cout * 9, dtype=torch.float32, device=x.device)
-    dw = torch.empty(cout, 1, 3, 3, dtype=torch.float32, device=x.device)
-    lib.cmu_conv3x3_c1_bn_wgrad(_ptr(x), _ptr(mask0), _ptr(da), _ptr(_act(y)), _ptr(scale), _ptr(shift), _ptr(mean),
-                                _ptr(rstd), _ptr(bn_partial), _ptr(sums), _ptr(wg_partial), _ptr(dw), n, h, wd,
-                                int(training), _stream())
-    return dw, sums[1], sums[0]
-
-
 # ------------------------------------------------------------------------------------------- BatchNorm2d
 def bn_finalize(stats, gamma, beta, conv_bias, running_mean, running_var, momentum, eps, training):
     """-> (scale, shift, mean, rstd), each (C,) fp32; updates the running statistics in place when training."""

@@ -65,13 +65,6 @@ int cmu_conv3x3_c1_wgrad(const float* x, const unsigned char* mask0, const void*
                          float* partial /* float[grid][576] */, float* dw /* (64,1,3,3) */, int accumulate, int n, int h,
                          int w_, void* stream);
 
-/* first-layer backward with BatchNorm + ReLU backward folded in (the 1-channel input needs no gradient, so wgrad is the
- * only consumer of dy, which is therefore never written): da = gradient of the activated output, y = raw conv output.
- * bn_partial: float[cmu_bn_bwd_grid()][128]; sums[2][64] = (dbeta, dgamma); wg_partial: float[cmu_conv3x3_c1_grid()][576]. */
-int cmu_conv3x3_c1_bn_wgrad(const float* x, const unsigned char* mask0, const void* da, const void* y, const float* scale,
-                            const float* shift, const float* mean, const float* rstd, float* bn_partial, float* sums,
-                            float* wg_partial, float* dw /* (64,1,3,3) */, int n, int h, int w_, int training, void* stream);
-
 /* conv3x3 pad 1 as tcgen05 implicit GEMM.  (x0|x1) = channel concat of two act tensors (munet_neck.py:48; x1 may be
  * NULL).  The conv bias is NOT applied (it cancels inside the train-mode BN that always follows; cmu_bn_finalize
  * folds it into running_mean / the eval shift).  stats_partial: float[*stats_grid][2][*stats_bn] per-CTA

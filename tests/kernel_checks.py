@@ -159,28 +159,6 @@ def check_conv3x3_c1(n=3, h=32, w=48, seed=1):
     return res
 
 
-def check_conv3x3_c1_bn_wgrad(n=3, h=30, w=52, seed=4):
-    """first-layer backward with the BatchNorm + ReLU backward folded into the weight-gradient kernel vs the two
-    stand-alone kernels (bn_relu_bwd -> conv3x3_c1_wgrad): same roundings, equal up to summation order."""
-    g = _gen(seed)
-    x = _randn((n, h, w), g)
-    mask0 = (torch.rand(h, w, generator=g) > 0.5).to(torch.uint8).to(DEV)
-    wt = _randn((64, 1, 3, 3), g, 0.3)
-    gamma = (torch.rand(64, generator=g) + 0.5).to(DEV)
-    beta = _randn((64,), g, 0.3)
-    da = nhwc(_randn((n, 64, h, w), g))
-    y, st = ops.conv3x3_c1_fprop(x, mask0, wt)
-    rm, rv = torch.zeros(64, device=DEV), torch.ones(64, device=DEV)
-    scale, shift, mean, rstd = ops.bn_finalize(st, gamma, beta, None, rm, rv, 0.1, 1e-5, True)
-    dy_u, dgamma_u, dbeta_u = ops.bn_relu_bwd(da, None, y, scale, shift, mean, rstd, True)
-    dw_u = ops.conv3x3_c1_wgrad(x, mask0, dy_u)
-    dw, dgamma, dbeta = ops.conv3x3_c1_bn_wgrad(x, mask0, da, y, scale, shift, mean, rstd, True)
-    torch.cuda.synchronize()
-    res = {'dw': rel_err(dw, dw_u), 'dgamma': rel_err(dgamma, dgamma_u), 'dbeta': rel_err(dbeta, dbeta_u)}
-    assert res['dw'] < 2e-5 and res['dgamma'] < 1e-6 and res['dbeta'] < 1e-6, res
-    return res
-
-
 # ------------------------------------------------------------------------------------------------ convT / 1x1
 def check_convT(n=2, h=12, w=20, cin=128, cout=64, seed=2, tol=1.5e-2):
     g = _gen(seed)
@@ -837,8 +815,6 @@ CHECKS = {
     'conv3x3_c1': check_conv3x3_c1,
     'conv3x3_c1_ragged_rows': lambda: check_conv3x3_c1(2, 30, 52, seed=2),   # H % 4 != 0, W % 32 != 0
     'conv3x3_c1_224': lambda: check_conv3x3_c1(2, 224, 224, seed=3),
-    'conv3x3_c1_bn_wgrad_fused': check_conv3x3_c1_bn_wgrad,
-    'conv3x3_c1_bn_wgrad_fused_224': lambda: check_conv3x3_c1_bn_wgrad(2, 224, 224, seed=5),
     'convT_128_64': lambda: check_convT(2, 12, 20, 128, 64),
     'convT_256_128_pair_ragged': lambda: check_convT(3, 120, 136, 256, 128, seed=15),
     'convT_512_256_pair': lambda: check_convT(17, 32, 32, 512, 256, seed=16),
