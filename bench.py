@@ -292,8 +292,6 @@ def run_ours(args):
     elif wl == 'moco':
         core = C.Moco_v2(emb_dim=1024, num_negatives=65536).to(dev).train()
         enc_q = ddp(core.encoder_q)                 # only the query encoder has gradients (moco2_module.py:140-146)
-        if world > 1:
-            core.encoder_q_ddp = enc_q
         opt = FusedSGD(core.encoder_q.named_parameters(), lr=0.03, momentum=0.9, weight_decay=1e-4)
         host_a = [torch.rand(B, S, S, generator=g).pin_memory() for _ in range(n_pool)]
         host_b = [torch.rand(B, S, S, generator=g).pin_memory() for _ in range(n_pool)]
