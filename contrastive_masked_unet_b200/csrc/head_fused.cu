@@ -27,7 +27,7 @@ __device__ __forceinline__ void unpack8h(const uint4& u, float (&f)[8]) {
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
 constexpr int kHeadC = 64;
-constexpr int kHeadRow = 2 * kHeadC + 2 * kHeadC + 2;   // partial row: sum dz [64], sum dz*xhat [64], dW [2][64], db [2]
+constexpr int kHeadRow = 2 * kHeadC + 2 * kHeadC + 2;   // partial row: sum dz [64], sum dz*y [64], dW [2][64], db [2]
 
 // a warp takes 32 consecutive pixels per iteration: 8 independent 16-byte loads per lane (4 pixels x 8 lanes each),
 // 8-lane butterflies, then lane L collects pixel L so that both output planes get one coalesced 128-byte store
@@ -63,10 +63,15 @@ __global__ void __launch_bounds__(256) bn_relu_head_fwd_kernel(const __nv_bfloat
       unpack8h(raw[j], f);
       float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float a = bf16_round(fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f));   // the activation the unfused path stored
-        d0 = fmaf(a, w0[k], d0);
-        d1 = fmaf(a, w1[k], d1);
+      for (int k = 0; k < 8; k += 2) {
+        // the activation the unfused path stored (bf16), two channels per conversion
+        const __nv_bfloat162 ab = __floats2bfloat162_rn(fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f),
+                                                        fmaxf(fmaf(f[k + 1], sc[k + 1], sh[k + 1]), 0.f));
+        const float2 a = __bfloat1622float2(ab);
+        d0 = fmaf(a.x, w0[k], d0);
+        d1 = fmaf(a.x, w1[k], d1);
+        d0 = fmaf(a.y, w0[k + 1], d0);
+        d1 = fmaf(a.y, w1[k + 1], d1);
       }
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
@@ -86,34 +91,53 @@ __global__ void __launch_bounds__(256) bn_relu_head_fwd_kernel(const __nv_bfloat
   }
 }
 
-// kApply = false: per-block partial row {sum dz, sum dz*xhat, dW_head, db_head}; kApply = true: dy.
+// bf16 rounding of a channel pair (what the unfused kernels stored), back in fp32
+__device__ __forceinline__ float2 round_bf16x2(float2 v) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+  return __bfloat1622float2(h);
+}
+
+// kApply = false: per-block partial row {sum dz, sum dz*y, dW_head, db_head}; kApply = true: dy.
+// Packed fp32 math (FFMA2): one instruction per channel PAIR.  The BatchNorm backward is evaluated in the algebraically
+// flattened form  dy = scale*dz + (A + B*y),  A = scale*(-k1 + k2*rstd*mean),  B = -scale*k2*rstd  (k1 = sum dz / n,
+// k2 = sum dz*xhat / n), and the reduce pass accumulates sum dz*y instead of sum dz*xhat (finished per channel in fp64 by
+// head_reduce_kernel: sum dz*xhat = rstd * (sum dz*y - mean * sum dz)): ~8 instructions per element instead of ~20 --
+// the first version of this kernel was instruction-bound at 2.4 TB/s.
 template <bool kApply>
-__global__ void __launch_bounds__(256) bn_head_bwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
-                                                          const float* __restrict__ shift, const float* __restrict__ mean,
-                                                          const float* __restrict__ rstd, const float* __restrict__ w,
-                                                          const float* __restrict__ dout, const float* __restrict__ sums,
-                                                          float inv_count, float* __restrict__ partial,
-                                                          __nv_bfloat16* __restrict__ dy, size_t npix, size_t hw) {
+__global__ void __launch_bounds__(256, 2) bn_head_bwd_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, const float* __restrict__ w,
+                                                             const float* __restrict__ dout, const float* __restrict__ sums,
+                                                             float inv_count, float* __restrict__ partial,
+                                                             __nv_bfloat16* __restrict__ dy, size_t npix, size_t hw) {
   __shared__ float sacc[kHeadRow];
   if (!kApply) {
     for (int i = threadIdx.x; i < kHeadRow; i += blockDim.x) sacc[i] = 0.f;
     __syncthreads();
   }
   const int cg = threadIdx.x & 7;
-  float w0[8], w1[8], sc[8], sh[8], mu[8], rs[8], k1[8], k2[8];
-  float a1[8], a2[8], g0[8], g1[8];
+  float2 w0[4], w1[4], sc[4], sh[4], cA[4], cB[4];
+  float2 a1[4], a2[4], g0[4], g1[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = cg * 8 + k;
-    w0[k] = w[c];
-    w1[k] = w[kHeadC + c];
-    sc[k] = scale[c];
-    sh[k] = shift[c];
-    mu[k] = mean[c];
-    rs[k] = rstd[c];
-    k1[k] = kApply ? sums[c] * inv_count : 0.f;
-    k2[k] = kApply ? sums[kHeadC + c] * inv_count : 0.f;
-    a1[k] = a2[k] = g0[k] = g1[k] = 0.f;
+  for (int k = 0; k < 4; ++k) {
+    const int c = cg * 8 + 2 * k;
+    w0[k] = make_float2(w[c], w[c + 1]);
+    w1[k] = make_float2(w[kHeadC + c], w[kHeadC + c + 1]);
+    sc[k] = make_float2(scale[c], scale[c + 1]);
+    sh[k] = make_float2(shift[c], shift[c + 1]);
+    if (kApply) {
+      float A[2], B[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float k1 = sums[c + e] * inv_count, k2 = sums[kHeadC + c + e] * inv_count;
+        const float s_ = scale[c + e], r_ = rstd[c + e], m_ = mean[c + e];
+        A[e] = s_ * (k2 * r_ * m_ - k1);
+        B[e] = -s_ * k2 * r_;
+      }
+      cA[k] = make_float2(A[0], A[1]);
+      cB[k] = make_float2(B[0], B[1]);
+    }
+    a1[k] = a2[k] = g0[k] = g1[k] = make_float2(0.f, 0.f);
   }
   float s0 = 0.f, s1 = 0.f;
   const uint32_t lane = threadIdx.x & 31;
@@ -142,48 +166,52 @@ __global__ void __launch_bounds__(256) bn_head_bwd_kernel(const __nv_bfloat16* _
       const bool in = pix < npix;
       const float d0 = __shfl_sync(0xffffffffu, dl0, j * 4 + (lane >> 3));   // 0 for out-of-range pixels
       const float d1 = __shfl_sync(0xffffffffu, dl1, j * 4 + (lane >> 3));
-      float f[8], o[8];
-      unpack8h(raw[j], f);
+      const float2 d0v = make_float2(d0, d0), d1v = make_float2(d1, d1);
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw[j]);
+      uint4 pk;
+      __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float a = bf16_round(fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f));
-        const float da = bf16_round(d0 * w0[k] + d1 * w1[k]);                // what the unfused head backward stored
-        const float dz = (in && a > 0.f) ? da : 0.f;
-        const float xh = (f[k] - mu[k]) * rs[k];
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __bfloat1622float2(hp[k]);
+        const float2 z = __ffma2_rn(f, sc[k], sh[k]);
+        const float2 da = round_bf16x2(__ffma2_rn(d0v, w0[k], __fmul2_rn(d1v, w1[k])));   // what head1x1_bwd stored
+        float2 dz;
+        dz.x = (in && z.x > 0.f) ? da.x : 0.f;
+        dz.y = (in && z.y > 0.f) ? da.y : 0.f;
         if (kApply) {
-          o[k] = sc[k] * (dz - k1[k] - xh * k2[k]);
+          const float2 o = __ffma2_rn(sc[k], dz, __ffma2_rn(cB[k], f, cA[k]));
+          ho[k] = __floats2bfloat162_rn(o.x, o.y);
         } else {
-          a1[k] += dz;
-          a2[k] = fmaf(dz, xh, a2[k]);
-          g0[k] = fmaf(d0, a, g0[k]);      // out-of-range pixels carry d = 0
-          g1[k] = fmaf(d1, a, g1[k]);
+          const float2 a = round_bf16x2(make_float2(fmaxf(z.x, 0.f), fmaxf(z.y, 0.f)));   // the activation bn_relu stored
+          a1[k] = __fadd2_rn(a1[k], dz);
+          a2[k] = __ffma2_rn(dz, f, a2[k]);
+          g0[k] = __ffma2_rn(d0v, a, g0[k]);      // out-of-range pixels carry d = 0
+          g1[k] = __ffma2_rn(d1v, a, g1[k]);
         }
       }
-      if (kApply && in) {
-        uint4 pk;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(o[2 * k], o[2 * k + 1]);
-        reinterpret_cast<uint4*>(dy)[pix * 8 + cg] = pk;
-      }
+      if (kApply && in) reinterpret_cast<uint4*>(dy)[pix * 8 + cg] = pk;
     }
     s0 += dl0;    // every pixel's dout is held by exactly one lane
     s1 += dl1;
   }
   if (!kApply) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float v[4] = {a1[k], a2[k], g0[k], g1[k]};
+    for (int k = 0; k < 4; ++k) {
+      float v[8] = {a1[k].x, a1[k].y, a2[k].x, a2[k].y, g0[k].x, g0[k].y, g1[k].x, g1[k].y};
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < 8; ++t) {
         v[t] += __shfl_xor_sync(0xffffffffu, v[t], 8);
         v[t] += __shfl_xor_sync(0xffffffffu, v[t], 16);
       }
       if (lane < 8) {
-        atomicAdd(&sacc[cg * 8 + k], v[0]);
-        atomicAdd(&sacc[kHeadC + cg * 8 + k], v[1]);
-        atomicAdd(&sacc[2 * kHeadC + cg * 8 + k], v[2]);
-        atomicAdd(&sacc[3 * kHeadC + cg * 8 + k], v[3]);
+        const int c = cg * 8 + 2 * k;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          atomicAdd(&sacc[c + e], v[0 + e]);
+          atomicAdd(&sacc[kHeadC + c + e], v[2 + e]);
+          atomicAdd(&sacc[2 * kHeadC + c + e], v[4 + e]);
+          atomicAdd(&sacc[3 * kHeadC + c + e], v[6 + e]);
+        }
       }
     }
 #pragma unroll
@@ -201,8 +229,9 @@ __global__ void __launch_bounds__(256) bn_head_bwd_kernel(const __nv_bfloat16* _
 }
 
 // out[c] = sum_r partial[r][c] in fp64, fixed order; columns [0,128) -> sums, [128,258) -> acc
-__global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restrict__ partial, int rows, float* __restrict__ sums,
-                                                          float* __restrict__ acc) {
+__global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restrict__ partial, int rows,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          float* __restrict__ sums, float* __restrict__ acc) {
   __shared__ double sred[8][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
@@ -215,8 +244,16 @@ __global__ void __launch_bounds__(256) head_reduce_kernel(const float* __restric
     double t = 0.0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += sred[k][cx];
-    if (c < 2 * kHeadC) sums[c] = (float)t;
-    else acc[c - 2 * kHeadC] = (float)t;
+    if (c < kHeadC) {
+      sums[c] = (float)t;                                         // sum dz
+    } else if (c < 2 * kHeadC) {
+      // sum dz*xhat = rstd * (sum dz*y - mean * sum dz): the sum dz of the same channel, reduced here again in fp64
+      double dz = 0.0;
+      for (int r = 0; r < rows; ++r) dz += partial[(size_t)r * kHeadRow + (c - kHeadC)];
+      sums[c] = (float)((double)rstd[c - kHeadC] * (t - (double)mean[c - kHeadC] * dz));
+    } else {
+      acc[c - 2 * kHeadC] = (float)t;
+    }
   }
 }
 
@@ -272,7 +309,7 @@ int cmu_bn_relu_head_bwd(const void* y, const float* scale, const float* shift, 
   bn_head_bwd_kernel<false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)y, scale, shift, mean, rstd, w, dout, nullptr, 0.f,
                                                   partial, nullptr, npix, hw);
   CMU_LAUNCH_CHECK();
-  head_reduce_kernel<<<ceil_div(kHeadRow, 32), 256, 0, st>>>(partial, grid, sums, acc);
+  head_reduce_kernel<<<ceil_div(kHeadRow, 32), 256, 0, st>>>(partial, grid, mean, rstd, sums, acc);
   CMU_LAUNCH_CHECK();
   bn_head_bwd_kernel<true><<<grid_apply, 256, 0, st>>>((const __nv_bfloat16*)y, scale, shift, mean, rstd, w, dout, sums, inv_count,
                                                  nullptr, (__nv_bfloat16*)dy, npix, hw);

@@ -309,7 +309,10 @@ def check_bn_relu_head(n=3, h=20, w=28, seed=21, training=True):
            'dhw_vs_unfused': rel_err(dhw, dhw_u), 'dhb_vs_unfused': rel_err(dhb, dhb_u),
            'fwd': rel_err(out, pr.detach()), 'dy': rel_err(nchw(dy), yin.grad), 'dgamma': rel_err(dgamma, gr.grad),
            'dbeta': rel_err(dbeta, br.grad), 'dhw': rel_err(dhw.reshape(2, c), hwr.grad.reshape(2, c)), 'dhb': rel_err(dhb, hbr.grad)}
-    assert max(res[k] for k in res if k.endswith('_vs_unfused')) < 2e-5, res
+    # dy is stored in bf16: the per-channel sums of the two paths differ in their last fp32 bit (atomics order), which can
+    # flip the rounding of single elements by one bf16 ulp -> 1e-3 of the largest element; everything else is fp32
+    assert res['dy_vs_unfused'] < 1e-3, res
+    assert max(res[k] for k in res if k.endswith('_vs_unfused') and k != 'dy_vs_unfused') < 2e-5, res
     assert res['fwd'] < 1e-2 and res['dy'] < 2e-2 and res['dgamma'] < 5e-3 and res['dbeta'] < 5e-3, res
     assert res['dhw'] < 5e-3 and res['dhb'] < 1e-5, res
     return res
