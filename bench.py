@@ -203,7 +203,7 @@ def workload_name(workload, B, S):
 
 
 # ---------------------------------------------------------------------------------------------------- library baseline
-def torch_library_step(B, S, steps=2, warmup=1):
+def torch_library_step(B, S, steps=3, warmup=2):
     """Same-box LIBRARY comparator: the oracle port run through torch on this GPU the way a user of the
     reference would run it on a B200 -- bf16 autocast, channels-last weights, cuDNN/cuBLAS kernels, torch.optim.AdamW
     (fused), host-side numpy mask generation exactly as the reference does it.  Not the target, a same-box peer."""
@@ -233,7 +233,7 @@ def torch_library_step(B, S, steps=2, warmup=1):
             ts.append(time.time() - t0)
     del m, opt
     torch.cuda.empty_cache()
-    return sum(ts) / len(ts)
+    return sorted(ts)[len(ts) // 2], ts
 
 
 # ---------------------------------------------------------------------------------------------------- our arm
@@ -510,16 +510,17 @@ def run_ours(args):
                 try:
                     lib_B = B
                     try:
-                        t_lib = torch_library_step(lib_B, S)
+                        t_lib, t_all = torch_library_step(lib_B, S)
                     except torch.OutOfMemoryError:
                         torch.cuda.empty_cache()
                         lib_B = B // 2
-                        t_lib = torch_library_step(lib_B, S)
+                        t_lib, t_all = torch_library_step(lib_B, S)
                     line['library_baseline'] = {
                         'value': lib_B / t_lib, 'unit': 'images/s', 'ms_per_step': t_lib * 1e3, 'per_step_batch': lib_B,
+                        'ms_all_timed_steps': [round(t * 1e3, 1) for t in t_all],
                         'what': 'the oracle port (== reference modules) through torch on the SAME GPU: bf16 autocast, '
                                 'channels-last weights, cuDNN/cuBLAS, fused torch AdamW, EMA, host numpy mask generation as '
-                                'in the reference; 1 warm-up + 2 timed steps, wall clock with synchronize'}
+                                'in the reference; 2 warm-up + 3 timed steps (median), wall clock with synchronize'}
                 except Exception as e:   # the comparator must never take the bench line down
                     line['library_baseline'] = {'unavailable': f'{type(e).__name__}: {str(e)[:120]}'}
             cores = os.cpu_count() or 1
