@@ -173,7 +173,8 @@ def run_reference(args):
     line = {'metric': metric_name(args.workload), 'value': val, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': steps,
             'warmup': warm, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': workload_name(args.workload, B, S) + ' -- CPU, bounded sample', 'per_step_batch': B,
+            'config': {'workload': workload_name(args.workload, {'pretrain': 64, 'moco': 64, 'finetune1024': 16}[args.workload], S) +
+                       f' -- reference CPU path, bounded sample of {B} images per step', 'per_step_batch': B,
                        'img_size': S, 'requested_steps': args.steps, 'requested_warmup': args.warmup,
                        'note': 'steps / warmup above are the counts actually run (bounded CPU sample)'},
             'cpu_baseline': {'value': val, 'unit': 'images/s', 'cores': torch.get_num_threads(), 'kind': 'port',
