@@ -8,9 +8,9 @@
 // The resize is Pillow's (`Image.resize(size, BICUBIC)`, libImaging/Resample.c), restated so that results are BIT-EXACT
 // with the reference for uint8 ("L": 22-bit fixed-point coefficients, int32 accumulation) and float32 ("F": double
 // accumulation in tap order, float32 store after each pass) images: horizontal pass, then vertical pass, coefficients
-// recomputed per output element in double precision (window [xmin, xmax), support 2 * max(scale, 1), normalised).
+// evaluated once per CTA in double precision (window [xmin, xmax), support 2 * max(scale, 1), normalised).
 // This file is compiled with -fmad=false: Pillow / numpy evaluate these expressions without fused multiply-adds and a
-// contracted FMA would change the last bit.  HBM-bound, tiny next to the training step (N = 64: ~0.1 ms).
+// contracted FMA would change the last bit.  Launch-latency bound and tiny next to the training step (N = 64: 0.3 ms).
 #include "common.cuh"
 #include "../../include/cmu_b200.h"
 
@@ -57,34 +57,44 @@ __device__ __forceinline__ double window_k(const Window& w, int x) {
 
 constexpr int kPrecisionBits = 32 - 8 - 2;
 
-template <typename T>
-__device__ __forceinline__ T resample_dot(const T* p, long long stride, const Window& w);
-
-template <>
-__device__ __forceinline__ unsigned char resample_dot<unsigned char>(const unsigned char* p, long long stride,
-                                                                      const Window& w) {
-  int acc = 1 << (kPrecisionBits - 1);
-  for (int x = 0; x < w.n; ++x) {
+// Coefficient of tap x in the form the accumulation uses: 22-bit fixed point (uint8) or double (float32)
+template <typename T> struct Coef;
+template <> struct Coef<unsigned char> {
+  typedef int type;
+  static __device__ __forceinline__ int make(const Window& w, int x) {
     const double k = window_k(w, x);
-    const int ki = k < 0 ? (int)(-0.5 + k * (1 << kPrecisionBits)) : (int)(0.5 + k * (1 << kPrecisionBits));
-    acc += (int)p[x * stride] * ki;
+    return k < 0 ? (int)(-0.5 + k * (1 << kPrecisionBits)) : (int)(0.5 + k * (1 << kPrecisionBits));
   }
-  acc >>= kPrecisionBits;
-  return (unsigned char)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
-}
-template <>
-__device__ __forceinline__ float resample_dot<float>(const float* p, long long stride, const Window& w) {
-  double acc = 0.0;
-  for (int x = 0; x < w.n; ++x) acc += (double)p[x * stride] * window_k(w, x);
-  return (float)acc;
-}
+  static __device__ __forceinline__ unsigned char finish(int acc) {
+    acc >>= kPrecisionBits;
+    return (unsigned char)(acc < 0 ? 0 : (acc > 255 ? 255 : acc));
+  }
+  static __device__ __forceinline__ int init() { return 1 << (kPrecisionBits - 1); }
+  static __device__ __forceinline__ int mac(int acc, unsigned char v, int k) { return acc + (int)v * k; }
+};
+template <> struct Coef<float> {
+  typedef double type;
+  static __device__ __forceinline__ double make(const Window& w, int x) { return window_k(w, x); }
+  static __device__ __forceinline__ float finish(double acc) { return (float)acc; }
+  static __device__ __forceinline__ double init() { return 0.0; }
+  static __device__ __forceinline__ double mac(double acc, float v, double k) { return acc + (double)v * k; }
+};
+
+constexpr int kMaxTaps = 16;     // windows up to 16 taps (down-scaling by <= 3.75) are staged; wider ones are recomputed
+constexpr int kFinalizeSplit = 8; // CTAs per sample in aug_finalize_kernel
+constexpr int kRowsPerCta = 32;  // horizontal pass: rows that share one coefficient evaluation
 
 // boxes: [n][4] = x0, y0, w, h (crop rectangle inside the src plane) or nullptr = the whole plane.
 // Horizontal: tmp[n][y][xx], y in [0, box.h), xx in [0, out_w).  Vertical: dst[n][yy][xx].
+// The coefficients depend on the output index along the resampled axis only, so they are evaluated ONCE per CTA --
+// per thread (its own xx) for kRowsPerCta rows in the horizontal pass, per CTA (one yy) in the vertical pass -- and the
+// per-element work is the tap loop alone.  Same values, same accumulation order as the per-element evaluation.
 template <typename T, bool HORIZ>
 __global__ void __launch_bounds__(256) pil_pass_kernel(const T* __restrict__ src, int src_h, int src_w,
                                                        const int* __restrict__ boxes, T* __restrict__ dst, int dst_h,
                                                        int dst_w, int tmp_h) {
+  typedef typename Coef<T>::type CT;
+  __shared__ CT s_k[HORIZ ? kMaxTaps * 256 : kMaxTaps];
   const int n = blockIdx.z;
   int x0 = 0, y0 = 0, bw = src_w, bh = src_h;
   if (boxes != nullptr) {
@@ -94,19 +104,40 @@ __global__ void __launch_bounds__(256) pil_pass_kernel(const T* __restrict__ src
     bh = boxes[4 * n + 3];
   }
   const int xx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int yy = blockIdx.y;
   if (HORIZ) {
     // src: the raw plane (src_h x src_w); dst: tmp plane (tmp_h x dst_w), rows of the crop
-    if (xx >= dst_w || yy >= bh) return;
+    const int y_lo = blockIdx.y * kRowsPerCta;
+    if (xx >= dst_w || y_lo >= bh) return;
+    const int y_hi = min(y_lo + kRowsPerCta, bh);
     const Window w = make_window(xx, bw, dst_w);
-    const T* p = src + ((size_t)n * src_h + (y0 + yy)) * src_w + x0 + w.xmin;
-    dst[((size_t)n * tmp_h + yy) * dst_w + xx] = resample_dot<T>(p, 1, w);
+    const bool staged = w.n <= kMaxTaps;
+    if (staged)
+      for (int x = 0; x < w.n; ++x) s_k[x * 256 + threadIdx.x] = Coef<T>::make(w, x);
+    for (int yy = y_lo; yy < y_hi; ++yy) {
+      const T* p = src + ((size_t)n * src_h + (y0 + yy)) * src_w + x0 + w.xmin;
+      CT acc = Coef<T>::init();
+      if (staged)
+        for (int x = 0; x < w.n; ++x) acc = Coef<T>::mac(acc, p[x], s_k[x * 256 + threadIdx.x]);
+      else
+        for (int x = 0; x < w.n; ++x) acc = Coef<T>::mac(acc, p[x], Coef<T>::make(w, x));
+      dst[((size_t)n * tmp_h + yy) * dst_w + xx] = Coef<T>::finish(acc);
+    }
   } else {
     // src: tmp plane (tmp_h x dst_w) holding bh valid rows; dst: (dst_h x dst_w)
-    if (xx >= dst_w || yy >= dst_h) return;
-    const Window w = make_window(yy, bh, dst_h);
+    const int yy = blockIdx.y;
+    if (yy >= dst_h) return;
+    const Window w = make_window(yy, bh, dst_h);     // identical in every thread of the CTA
+    const bool staged = w.n <= kMaxTaps;
+    if (staged && (int)threadIdx.x < w.n) s_k[threadIdx.x] = Coef<T>::make(w, threadIdx.x);
+    __syncthreads();
+    if (xx >= dst_w) return;
     const T* p = src + ((size_t)n * tmp_h + w.xmin) * dst_w + xx;
-    dst[((size_t)n * dst_h + yy) * dst_w + xx] = resample_dot<T>(p, dst_w, w);
+    CT acc = Coef<T>::init();
+    if (staged)
+      for (int x = 0; x < w.n; ++x) acc = Coef<T>::mac(acc, p[(size_t)x * dst_w], s_k[x]);
+    else
+      for (int x = 0; x < w.n; ++x) acc = Coef<T>::mac(acc, p[(size_t)x * dst_w], Coef<T>::make(w, x));
+    dst[((size_t)n * dst_h + yy) * dst_w + xx] = Coef<T>::finish(acc);
   }
 }
 
@@ -138,7 +169,8 @@ template <typename T>
 __device__ __forceinline__ float to_f32(T v) { return (float)v; }
 
 // ShiftPixel (processing.py:109-121) on the horizontally flipped (or not) 256 x 256 image + GaussNoise
-// (auto_augment.py:1148-1154).  One CTA per sample.  params: [n][4] = flip, ph, pw, unused.
+// (auto_augment.py:1148-1154).  gridDim.y CTAs per sample: each finds the block maximum itself (the 200 KB crop is read
+// from L2) and writes its share of the pixels.  params: [n][4] = flip, ph, pw, unused.
 template <typename T>
 __global__ void __launch_bounds__(256) aug_finalize_kernel(const T* __restrict__ src, int sh, int sw,
                                                            const int* __restrict__ params,
@@ -166,7 +198,7 @@ __global__ void __launch_bounds__(256) aug_finalize_kernel(const T* __restrict__
   double sigma;
   if (sizeof(T) == 1) sigma = (double)mx / 10.0;
   else sigma = (double)(mx / 10.0f);
-  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < total; i += blockDim.x * gridDim.y) {
     const int y = i / crop, x = i - y * crop;
     const int x_a = flip ? (sw - 1 - x) : x;                 // ShiftPixel(pixel = 0)
     const int x_b = flip ? (sw - 1 - (pw + x)) : (pw + x);   // ShiftPixel(pixel = 31) draw (ph, pw)
@@ -185,7 +217,7 @@ template <typename T>
 static int run_resize(const void* src, int n, int src_h, int src_w, const int* boxes, void* tmp, void* dst, int out_h,
                       int out_w, cudaStream_t st) {
   dim3 block(256);
-  dim3 gh(ceil_div(out_w, 256), src_h, n);
+  dim3 gh(ceil_div(out_w, 256), ceil_div(src_h, kRowsPerCta), n);
   pil_pass_kernel<T, true><<<gh, block, 0, st>>>((const T*)src, src_h, src_w, boxes, (T*)tmp, out_h, out_w, src_h);
   CMU_LAUNCH_CHECK();
   dim3 gv(ceil_div(out_w, 256), out_h, n);
@@ -220,10 +252,10 @@ int cmu_aug_shift_flip_noise(const void* src, int dtype, int n, int src_h, int s
   CMU_REQUIRE(n > 0 && crop > 0 && crop + 31 < src_h + 1 && crop <= src_w, "aug: bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == 0)
-    aug_finalize_kernel<unsigned char><<<n, 256, 0, st>>>((const unsigned char*)src, src_h, src_w, d_params, noise, seed,
+    aug_finalize_kernel<unsigned char><<<dim3(n, kFinalizeSplit), 256, 0, st>>>((const unsigned char*)src, src_h, src_w, d_params, noise, seed,
                                                           crop, img, img_t);
   else
-    aug_finalize_kernel<float><<<n, 256, 0, st>>>((const float*)src, src_h, src_w, d_params, noise, seed, crop, img, img_t);
+    aug_finalize_kernel<float><<<dim3(n, kFinalizeSplit), 256, 0, st>>>((const float*)src, src_h, src_w, d_params, noise, seed, crop, img, img_t);
   CMU_LAUNCH_CHECK();
   return 0;
 }
