@@ -82,6 +82,27 @@ def misc():
           f'+plain {t4:.3f} ms ({8 * xb / t4 / 1e9:.2f} TB/s)', flush=True)
 
 
+def head():
+    """fused decoder tail (csrc/head_fused.cu) at the benchmark shape"""
+    dev = 'cuda'
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    B, S, C = 64, 512, 64
+    y = torch.randn(B, S, S, C, device=dev).to(BF16)
+    scale, shift = torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev) * 0.1
+    mean, rstd = torch.randn(C, device=dev) * 0.1, torch.rand(C, device=dev) + 0.5
+    w, b = torch.randn(2, C, device=dev), torch.randn(2, device=dev)
+    dout = torch.randn(B, 2, S, S, device=dev)
+    nb, ob = y.numel() * 2, dout.numel() * 4
+    t1 = timeit(lambda: ops.bn_relu_head_fwd(y, scale, shift, w, b), flush)
+    t2 = timeit(lambda: ops.bn_relu_head_bwd(y, scale, shift, mean, rstd, w, dout), flush)
+    print(f'fused tail fwd {t1:.3f} ms ({(nb + ob) / t1 / 1e9:.2f} TB/s: y read, out written)  '
+          f'bwd (reduce + apply) {t2:.3f} ms ({(3 * nb + 2 * ob) / t2 / 1e9:.2f} TB/s: y, dout read twice, dy written)', flush=True)
+
+
 if __name__ == '__main__':
-    misc()
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'head':
+        head()
+    else:
+        misc()
+        main()
+        head()
